@@ -1,0 +1,80 @@
+"""The canonical-fp32 top-k oracle (oracle/topk_ref.c) against an independent float64 brute force."""
+import numpy as np
+
+from oracle import topk_ref as T
+
+
+def _data(n, q, seed, dup=0):
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(n, 16)).astype(np.float32)
+    if dup:
+        src = rng.integers(0, n, size=dup)
+        dst = rng.integers(0, n, size=dup)
+        d[dst] = d[src]
+    qs = d[rng.integers(0, n, size=q)] + 0.05 * rng.normal(size=(q, 16)).astype(np.float32)
+    return d, qs.astype(np.float32)
+
+
+def test_normalize_rows():
+    d, _ = _data(1000, 1, 0)
+    d[5] = 0.0
+    dn = T.normalize_rows(d)
+    np.testing.assert_array_equal(dn[5], 0.0)  # zero norm -> divided by 1 (faiss_db.py:111-112)
+    ref = d.astype(np.float64) / np.maximum(np.linalg.norm(d.astype(np.float64), axis=1, keepdims=True), 1e-300)
+    ref[5] = 0
+    np.testing.assert_allclose(dn, ref, rtol=3e-7, atol=0)
+
+
+def test_topk_agrees_with_float64_bruteforce_up_to_near_ties():
+    d, q = _data(20000, 128, 1)
+    dn, qn = T.normalize_rows(d), T.normalize_rows(q)
+    dots, idx = T.topk(dn, qn, 10)
+    s = qn.astype(np.float64) @ dn.astype(np.float64).T
+    ref = np.argsort(-s, axis=1, kind="stable")[:, :10]
+    assert (np.diff(dots, axis=1) <= 0).all()
+    mism = idx != ref
+    # where the ordered lists differ the float64 scores must be within fp32 rounding of each other
+    for qi, pos in zip(*np.where(mism)):
+        assert abs(s[qi, idx[qi, pos]] - s[qi, ref[qi, pos]]) < 4e-7
+    assert mism.mean() < 0.01
+    np.testing.assert_allclose(dots, np.take_along_axis(s, idx, 1), atol=3e-7)
+
+
+def test_ties_break_on_lower_global_index_and_index_base():
+    d, q = _data(5000, 32, 2, dup=500)
+    d[100:110] = d[7]  # ten exact copies of one row
+    q[0] = d[7]
+    dn, qn = T.normalize_rows(d), T.normalize_rows(q)
+    dots, idx = T.topk(dn, qn, 10, index_base=1000)
+    assert idx[0, 0] == 1007 and list(idx[0, 1:]) == list(range(1100, 1109))
+    assert (dots[0] == dots[0, 0]).all()
+    # order inside every list: dot desc, idx asc
+    for a in range(idx.shape[0]):
+        for b in range(9):
+            assert dots[a, b] > dots[a, b + 1] or (dots[a, b] == dots[a, b + 1] and idx[a, b] < idx[a, b + 1])
+
+
+def test_small_dictionary_and_merge():
+    d, q = _data(7, 3, 3)
+    dn, qn = T.normalize_rows(d), T.normalize_rows(q)
+    dots, idx = T.topk(dn, qn, 10)
+    assert (idx[:, 7:] == -1).all() and np.isinf(dots[:, 7:]).all()
+    assert sorted(idx[0, :7]) == list(range(7))
+    # row-sharded search + merge == one search
+    d2, q2 = _data(3001, 17, 4, dup=100)
+    dn, qn = T.normalize_rows(d2), T.normalize_rows(q2)
+    full = T.topk(dn, qn, 10)
+    cuts = [0, 1000, 1001, 2500, 3001]
+    parts = [T.topk(dn[a:b], qn, 10, index_base=a) for a, b in zip(cuts[:-1], cuts[1:])]
+    md, mi = T.topk_merge(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]))
+    np.testing.assert_array_equal(mi, full[1])
+    np.testing.assert_array_equal(md, full[0])
+
+
+def test_threads_do_not_change_results():
+    d, q = _data(4000, 64, 5)
+    dn, qn = T.normalize_rows(d), T.normalize_rows(q)
+    a = T.topk(dn, qn, 10, nthreads=1)
+    b = T.topk(dn, qn, 10, nthreads=4)
+    np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_array_equal(a[0], b[0])
