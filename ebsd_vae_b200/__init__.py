@@ -1,0 +1,34 @@
+"""ebsd_vae_b200 -- B200-native dictionary-indexing hot path behind the ``latice`` API.
+
+Drop-in names (reference: poyentung/ebsd-vae, package ``latice``):
+
+* ``DiffractionPatternIndexer``, ``IndexerConfig``           (latice/index/dp_indexer.py)
+* ``LatentVectorDatabase`` (= ``ChromaLatentVectorDatabase``), ``LatentVectorDatabaseConfig``,
+  ``OrientationResult``                                      (latice/index/chroma_db.py)
+* ``VariationalAutoEncoderRawData``                          (latice/model.py)
+
+All compute runs in libebsd_b200.so (hand-written sm_100a CUDA behind a C ABI, include/ebsd_b200.h).
+There is no CPU or eager-PyTorch fallback.
+"""
+from .dp_indexer import DiffractionPatternIndexer, IndexerConfig
+from .model import EncoderEngine, VariationalAutoEncoderRawData, load_vae_weights
+from .vector_db import (
+    ChromaLatentVectorDatabase,
+    LatentVectorDatabase,
+    LatentVectorDatabaseConfig,
+    OrientationResult,
+    OrientationResultBatch,
+)
+
+__all__ = [
+    "DiffractionPatternIndexer",
+    "IndexerConfig",
+    "EncoderEngine",
+    "VariationalAutoEncoderRawData",
+    "load_vae_weights",
+    "ChromaLatentVectorDatabase",
+    "LatentVectorDatabase",
+    "LatentVectorDatabaseConfig",
+    "OrientationResult",
+    "OrientationResultBatch",
+]

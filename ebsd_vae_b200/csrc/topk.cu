@@ -1,0 +1,531 @@
+// K2: exact cosine top-k over the 16-D latent dictionary (canonical fp32, see oracle/topk_ref.c).
+//
+// Replaces FaissLatentVectorDatabase.query_similar / _l2_normalize (latice/index/faiss_db.py:109-113,216-256)
+// and ChromaLatentVectorDatabase.query_similar (latice/index/chroma_db.py:231-259).
+//
+// Shape of the kernel
+//   * persistent CTAs (one per SM) walk work items (query tile, dictionary split);
+//   * one elected thread streams 128-row dictionary tiles (8 KiB) into a 4-stage shared-memory ring with TMA
+//     (cp.async.bulk.tensor.2d, SWIZZLE_64B so that the consumers' LDS.128 are bank-conflict free); it runs
+//     kStages-1 tiles ahead of the consumers and is itself lane 0 of warp 0 (a ninth warp would cost the
+//     other eight a third of their register budget);
+//   * 8 warps each own 2*TQ queries; a thread holds a TQ x 8 register tile of dot products,
+//     accumulated as fma chains in ascending j (bit-identical to the oracle);
+//   * selection: every dot is compared with the query's current k-th best (tau, in registers); the rare
+//     survivors go through a warp-private candidate buffer into a sorted per-query list (one entry per lane,
+//     ballot + shuffle insertion).  No CTA-wide synchronisation in the steady state.
+//   * ties: dot descending, then row index ascending -- rows arrive in ascending order and tau only lets
+//     strictly larger dots through once the list is full, which is exactly that rule.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ebsd {
+
+constexpr int kD = 16;
+constexpr int kTileRows = 128;
+constexpr int kTileBytes = kTileRows * kD * 4;
+constexpr int kStages = 4;
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kListLen = 32;                    // one entry per lane; k <= 32
+constexpr int kCandCap = 16;                    // survivors per query per 16-row sub-step
+constexpr int kIdxEmpty = 0x7fffffff;
+
+struct __align__(8) Entry {
+    float dot;
+    int idx;
+};
+
+__device__ __forceinline__ bool beats(float da, long long ia, float db, long long ib) {
+    return (da > db) || (da == db && ia < ib);
+}
+
+// Insert candidate (cd, ci) into the warp-distributed sorted list (lane l holds entry l).
+template <typename IdxT>
+__device__ __forceinline__ void warp_insert(float &e_dot, IdxT &e_idx, float cd, IdxT ci, int lane) {
+    const bool mine = beats(e_dot, (long long)e_idx, cd, (long long)ci);
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    const int pos = __popc(m);  // the list is sorted, so `mine` is true on a prefix of lanes
+    const float up_dot = __shfl_up_sync(0xffffffffu, e_dot, 1);
+    const IdxT up_idx = __shfl_up_sync(0xffffffffu, e_idx, 1);
+    if (lane == pos) {
+        e_dot = cd;
+        e_idx = ci;
+    } else if (lane > pos) {
+        e_dot = up_dot;
+        e_idx = up_idx;
+    }
+}
+
+struct TopkParams {
+    const float *queries;  // [Q,16] normalised
+    long long Q;
+    long long N;
+    long long index_base;
+    int k;
+    int n_qtiles;
+    int n_splits;
+    int tiles_per_split;   // dictionary tiles per split (last split may be shorter)
+    Entry *parts;          // [S,Q,k] when n_splits > 1
+    float *out_dot;        // [Q,k] when n_splits == 1
+    long long *out_idx;
+    float *out_dist;
+};
+
+template <int TQ>
+struct Smem {
+    static constexpr int QT = kWarps * 2 * TQ;
+    static constexpr int off_dtile = 0;
+    static constexpr int off_qtile = off_dtile + kStages * kTileBytes;
+    static constexpr int off_list = off_qtile + QT * kD * 4;
+    static constexpr int off_cand = off_list + QT * kListLen * 8;
+    static constexpr int off_cnt = off_cand + QT * kCandCap * 8;
+    static constexpr int off_tau = off_cnt + QT * 4;
+    static constexpr int off_bar = off_tau + QT * 4;
+    static constexpr int bytes = off_bar + 2 * kStages * 8;
+    static constexpr int alloc = bytes + 1024;  // slack for manual 1024-byte alignment
+};
+
+template <int TQ>
+__global__ void __launch_bounds__(kThreads, 1)
+topk_kernel(const __grid_constant__ CUtensorMap dict_map, const TopkParams p) {
+    using S = Smem<TQ>;
+    constexpr int QT = S::QT;
+    constexpr int QPW = 2 * TQ;  // queries per warp
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float *qtile = (float *)(smem + S::off_qtile);
+    Entry *lists = (Entry *)(smem + S::off_list);
+    Entry *cands = (Entry *)(smem + S::off_cand);
+    int *cnt = (int *)(smem + S::off_cnt);
+    float *tau_s = (float *)(smem + S::off_tau);
+    uint64_t *full_bar = (uint64_t *)(smem + S::off_bar);
+    uint64_t *empty_bar = full_bar + kStages;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kWarps);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&dict_map);
+    }
+    __syncthreads();
+
+    const long long total_tiles = (p.N + kTileRows - 1) / kTileRows;
+    const int n_items = p.n_qtiles * p.n_splits;
+    unsigned it = 0;  // running tile counter of this CTA: ring stage/phase bookkeeping (same on every warp)
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int split = item / p.n_qtiles;
+        const int qt = item - split * p.n_qtiles;
+        const long long tile0 = (long long)split * p.tiles_per_split;
+        long long tile1 = tile0 + p.tiles_per_split;
+        if (tile1 > total_tiles) tile1 = total_tiles;
+        const int ntiles = (int)(tile1 > tile0 ? tile1 - tile0 : 0);
+        const long long q0 = (long long)qt * QT;
+
+        // ---- stage the query tile and reset the per-query state
+        {
+            // smem layout: query (w, qg, qi) lives at row (w*TQ + qi)*2 + qg so that the two lane halves of a
+            // warp read different banks.
+            for (int v = tid; v < QT * 4; v += kWarps * 32) {
+                const int ql = v >> 2, c = v & 3;  // query within tile (w*QPW + qg*TQ + qi), 16-byte chunk
+                const int w = ql / QPW, r = ql - w * QPW, qg = r / TQ, qi = r - qg * TQ;
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q0 + ql < p.Q) val = *(const float4 *)(p.queries + (q0 + ql) * kD + c * 4);
+                *(float4 *)(qtile + (((w * TQ + qi) * 2 + qg) * kD) + c * 4) = val;
+            }
+            for (int v = tid; v < QT * kListLen; v += kWarps * 32) {
+                lists[v].dot = -INFINITY;
+                lists[v].idx = kIdxEmpty;
+            }
+            for (int v = tid; v < QT; v += kWarps * 32) {
+                cnt[v] = 0;
+                tau_s[v] = -INFINITY;
+            }
+        }
+        __syncthreads();
+
+        // Producer duty (warp 0, lane 0): tile t of this item goes to ring slot (it + t) % kStages.
+        auto issue_tile = [&](int t) {
+            const unsigned pit = it + (unsigned)t;
+            const int s = pit % kStages;
+            const unsigned ph = (pit / kStages) & 1u;
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            mbar_expect_tx(&full_bar[s], kTileBytes);
+            tma_load_2d(smem + S::off_dtile + s * kTileBytes, &dict_map, 0, (int)((tile0 + t) * kTileRows),
+                        &full_bar[s]);
+        };
+        if (tid == 0) {
+            for (int t = 0; t < kStages - 1 && t < ntiles; ++t) issue_tile(t);
+        }
+        {
+            const int qg = lane >> 4;   // which half of the warp's queries
+            const int dg = lane & 15;   // rows dg + 16*i of every tile
+            const int wq0 = warp * QPW; // first query (tile-local) of this warp
+            const int swz = (dg >> 1) & 3;
+            float tau[TQ];
+#pragma unroll
+            for (int qi = 0; qi < TQ; ++qi) tau[qi] = -INFINITY;
+
+            unsigned cit = it;
+            for (int t = 0; t < ntiles; ++t, ++cit) {
+                const int s = cit % kStages;
+                const unsigned ph = (cit / kStages) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                const float4 *dt = (const float4 *)(smem + S::off_dtile + s * kTileBytes);
+
+                float acc[TQ][8];
+#pragma unroll
+                for (int qi = 0; qi < TQ; ++qi)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[qi][i] = 0.f;
+
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float4 dv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dv[i] = dt[(dg + 16 * i) * 4 + (c ^ swz)];
+#pragma unroll
+                    for (int qi = 0; qi < TQ; ++qi) {
+                        const float4 qv = *(const float4 *)(qtile + (((warp * TQ + qi) * 2 + qg) * kD) + c * 4);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float a = acc[qi][i];
+                            a = fmaf(qv.x, dv[i].x, a);
+                            a = fmaf(qv.y, dv[i].y, a);
+                            a = fmaf(qv.z, dv[i].z, a);
+                            a = fmaf(qv.w, dv[i].w, a);
+                            acc[qi][i] = a;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+                if (tid == 0 && t + kStages - 1 < ntiles) issue_tile(t + kStages - 1);
+
+                // ---- selection: fast reject against tau, slow path only when something survives
+                bool hit = false;
+#pragma unroll
+                for (int qi = 0; qi < TQ; ++qi)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) hit |= acc[qi][i] > tau[qi];
+
+                if (__any_sync(0xffffffffu, hit)) {
+                    const long long row_base = (tile0 + t) * kTileRows;  // shard-local row of tile row 0
+                    long long valid_ll = p.N - row_base;
+                    const int valid = valid_ll > kTileRows ? kTileRows : (int)valid_ll;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = dg + 16 * i;
+                        bool pushed = false;
+                        if (row < valid) {
+#pragma unroll
+                            for (int qi = 0; qi < TQ; ++qi) {
+                                if (acc[qi][i] > tau[qi]) {
+                                    const int ql = wq0 + qg * TQ + qi;
+                                    const int slot = atomicAdd(&cnt[ql], 1);
+                                    Entry e;
+                                    e.dot = acc[qi][i];
+                                    e.idx = (int)(row_base + row);
+                                    cands[ql * kCandCap + slot] = e;
+                                    pushed = true;
+                                }
+                            }
+                        }
+                        if (__any_sync(0xffffffffu, pushed)) {
+                            __syncwarp();
+                            for (int ql = wq0; ql < wq0 + QPW; ++ql) {
+                                const int c = cnt[ql];
+                                if (c == 0) continue;
+                                Entry e = lists[ql * kListLen + lane];
+                                for (int j = 0; j < c; ++j) {
+                                    const Entry cd = cands[ql * kCandCap + j];
+                                    warp_insert<int>(e.dot, e.idx, cd.dot, cd.idx, lane);
+                                }
+                                lists[ql * kListLen + lane] = e;
+                                if (lane == p.k - 1) tau_s[ql] = e.dot;
+                                if (lane == 0) cnt[ql] = 0;
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int qi = 0; qi < TQ; ++qi) tau[qi] = tau_s[wq0 + qg * TQ + qi];
+                        }
+                    }
+                }
+            }
+
+            // ---- write this warp's lists
+            __syncwarp();
+            for (int ql = wq0; ql < wq0 + QPW; ++ql) {
+                const long long qglob = q0 + ql;
+                if (qglob >= p.Q || lane >= p.k) continue;
+                const Entry e = lists[ql * kListLen + lane];
+                if (p.n_splits > 1) {
+                    p.parts[((long long)split * p.Q + qglob) * p.k + lane] = e;
+                } else {
+                    const bool empty = e.idx == kIdxEmpty;
+                    p.out_dot[qglob * p.k + lane] = e.dot;
+                    p.out_idx[qglob * p.k + lane] = empty ? -1ll : p.index_base + e.idx;
+                    if (p.out_dist) p.out_dist[qglob * p.k + lane] = 1.0f - e.dot;
+                }
+            }
+        }
+        it += (unsigned)ntiles;
+        __syncthreads();
+    }
+}
+
+// Merge S partial lists per query (one warp per query). Partials hold shard-local int rows.
+__global__ void topk_merge_parts_kernel(const Entry *parts, int S, long long Q, int k, long long index_base,
+                                        float *out_dot, long long *out_idx, float *out_dist) {
+    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    float e_dot = -INFINITY;
+    int e_idx = kIdxEmpty;
+    for (int s = 0; s < S; ++s) {
+        const Entry *src = parts + ((long long)s * Q + q) * k;
+        for (int j = 0; j < k; ++j) {
+            const Entry cd = src[j];
+            if (cd.idx == kIdxEmpty) break;  // lists are sorted, empties are at the tail
+            warp_insert<int>(e_dot, e_idx, cd.dot, cd.idx, lane);
+        }
+    }
+    if (lane < k) {
+        out_dot[q * k + lane] = e_dot;
+        out_idx[q * k + lane] = e_idx == kIdxEmpty ? -1ll : index_base + e_idx;
+        if (out_dist) out_dist[q * k + lane] = 1.0f - e_dot;
+    }
+}
+
+// Merge R per-shard lists with global int64 indices (K2m, runs after the all-gather).
+__global__ void topk_merge_global_kernel(const float *dots, const long long *idx, int R, long long Q, int k,
+                                         float *out_dot, long long *out_idx, float *out_dist) {
+    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    float e_dot = -INFINITY;
+    long long e_idx = 0x7fffffffffffffffll;
+    for (int r = 0; r < R; ++r) {
+        const long long base = ((long long)r * Q + q) * k;
+        for (int j = 0; j < k; ++j) {
+            const long long ci = idx[base + j];
+            if (ci < 0) break;
+            warp_insert<long long>(e_dot, e_idx, dots[base + j], ci, lane);
+        }
+    }
+    if (lane < k) {
+        const bool empty = e_idx == 0x7fffffffffffffffll;
+        out_dot[q * k + lane] = e_dot;
+        out_idx[q * k + lane] = empty ? -1ll : e_idx;
+        if (out_dist) out_dist[q * k + lane] = 1.0f - e_dot;
+    }
+}
+
+// x[i,:] /= ||x[i,:]||, canonical arithmetic (fma chain, IEEE sqrt and division).
+__global__ void normalize_rows_kernel(float *x, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 *row = (float4 *)(x + i * kD);
+    float4 v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = row[c];
+    float n2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        n2 = fmaf(v[c].x, v[c].x, n2);
+        n2 = fmaf(v[c].y, v[c].y, n2);
+        n2 = fmaf(v[c].z, v[c].z, n2);
+        n2 = fmaf(v[c].w, v[c].w, n2);
+    }
+    float norm = __fsqrt_rn(n2);
+    if (norm == 0.f) norm = 1.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        v[c].x = __fdiv_rn(v[c].x, norm);
+        v[c].y = __fdiv_rn(v[c].y, norm);
+        v[c].z = __fdiv_rn(v[c].z, norm);
+        v[c].w = __fdiv_rn(v[c].w, norm);
+        row[c] = v[c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct TopkPlan {
+    int tq;               // queries per thread (8 or 1)
+    int qt;               // queries per CTA
+    int n_qtiles;
+    int n_splits;
+    int tiles_per_split;
+};
+
+static TopkPlan make_plan(long long N, long long Q, int sms) {
+    TopkPlan pl;
+    pl.tq = Q <= 16 ? 1 : 8;
+    pl.qt = kWarps * 2 * pl.tq;
+    pl.n_qtiles = (int)((Q + pl.qt - 1) / pl.qt);
+    const long long total_tiles = (N + kTileRows - 1) / kTileRows;
+    // Choose the number of dictionary splits: fill whole waves of `sms` persistent CTAs while keeping each
+    // split long enough to amortise the warm-up of the selection (tau starts at -inf in every split).
+    const double overhead_tiles = 24.0;
+    int best_s = 1;
+    double best_eff = -1.0;
+    const long long max_s = total_tiles < 1 ? 1 : (total_tiles < 4096 ? total_tiles : 4096);
+    for (long long s = 1; s <= max_s && s <= 4096; ++s) {
+        const long long tps = (total_tiles + s - 1) / s;
+        if (tps < 4 && s > 1) break;
+        const long long s_eff = (total_tiles + tps - 1) / tps;  // splits actually used
+        const long long items = (long long)pl.n_qtiles * s_eff;
+        const long long waves = (items + sms - 1) / sms;
+        const double eff = ((double)items / (double)(waves * sms)) * ((double)tps / ((double)tps + overhead_tiles));
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best_s = (int)s_eff;
+        }
+        if (items >= 16ll * sms) break;
+    }
+    pl.n_splits = best_s;
+    pl.tiles_per_split = (int)((total_tiles + best_s - 1) / best_s);
+    if (pl.tiles_per_split < 1) pl.tiles_per_split = 1;
+    pl.n_splits = (int)((total_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split);
+    if (pl.n_splits < 1) pl.n_splits = 1;
+    return pl;
+}
+
+template <int TQ>
+static int launch_topk(const CUtensorMap &map, const TopkParams &p, int sms, cudaStream_t st) {
+    using S = Smem<TQ>;
+    static bool configured = false;
+    if (!configured) {
+        EBSD_CUDA_TRY(cudaFuncSetAttribute(topk_kernel<TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::alloc));
+        configured = true;
+    }
+    const int n_items = p.n_qtiles * p.n_splits;
+    const int grid = n_items < sms ? n_items : sms;
+    topk_kernel<TQ><<<grid, kThreads, S::alloc, st>>>(map, p);
+    EBSD_CUDA_TRY(cudaGetLastError());
+    return EBSD_OK;
+}
+
+}  // namespace ebsd
+
+using namespace ebsd;
+
+extern "C" {
+
+int ebsd_normalize_rows(float *x, int64_t n, int d, void *stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    EBSD_REQUIRE(d == kD, "ebsd_normalize_rows: d must be %d, got %d", kD, d);
+    EBSD_REQUIRE(n >= 0, "ebsd_normalize_rows: negative n");
+    EBSD_REQUIRE(n == 0 || x != nullptr, "ebsd_normalize_rows: null pointer");
+    EBSD_REQUIRE(((uintptr_t)x & 15) == 0, "ebsd_normalize_rows: x must be 16-byte aligned");
+    if (n == 0) return EBSD_OK;
+    const int threads = 256;
+    normalize_rows_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(x, n);
+    EBSD_CUDA_TRY(cudaGetLastError());
+    return EBSD_OK;
+}
+
+size_t ebsd_topk_workspace_bytes(int64_t N, int64_t Q, int k) {
+    if (N <= 0 || Q <= 0 || k <= 0) return 0;
+    const TopkPlan pl = make_plan(N, Q, sm_count());
+    return pl.n_splits > 1 ? (size_t)pl.n_splits * (size_t)Q * (size_t)k * sizeof(Entry) : 0;
+}
+
+int ebsd_topk(const float *dict, int64_t N, int64_t index_base, const float *queries, int64_t Q, int k,
+              float *out_dot, int64_t *out_idx, float *out_dist, void *workspace, size_t workspace_bytes,
+              void *stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    EBSD_REQUIRE(k >= 1 && k <= EBSD_MAX_TOPK, "ebsd_topk: k must be in [1,%d], got %d", EBSD_MAX_TOPK, k);
+    EBSD_REQUIRE(N >= 0 && Q >= 0, "ebsd_topk: negative size");
+    EBSD_REQUIRE(N < 0x7fffff00ll, "ebsd_topk: a shard holds at most 2^31-257 rows");
+    if (Q == 0) return EBSD_OK;
+    EBSD_REQUIRE(queries && out_dot && out_idx, "ebsd_topk: null pointer");
+    EBSD_REQUIRE(((uintptr_t)queries & 15) == 0, "ebsd_topk: queries must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) {
+        const int wpb = 8;
+        topk_merge_global_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+            nullptr, nullptr, 0, Q, k, out_dot, (long long *)out_idx, out_dist);
+        EBSD_CUDA_TRY(cudaGetLastError());
+        return EBSD_OK;
+    }
+    EBSD_REQUIRE(dict != nullptr, "ebsd_topk: null dictionary");
+    EBSD_REQUIRE(((uintptr_t)dict & 15) == 0, "ebsd_topk: dict must be 16-byte aligned");
+
+    const int sms = sm_count();
+    const TopkPlan pl = make_plan(N, Q, sms);
+    const size_t need = pl.n_splits > 1 ? (size_t)pl.n_splits * (size_t)Q * (size_t)k * sizeof(Entry) : 0;
+    if (need > 0 && (workspace == nullptr || workspace_bytes < need)) {
+        set_error("ebsd_topk: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return EBSD_ERR_WORKSPACE;
+    }
+
+    tensormap_encode_fn encode = get_tensormap_encode();
+    if (!encode) {
+        set_error("ebsd_topk: cuTensorMapEncodeTiled entry point not available");
+        return EBSD_ERR_CUDA;
+    }
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = {(cuuint64_t)kD, (cuuint64_t)N};
+    const cuuint64_t gstride[1] = {(cuuint64_t)(kD * 4)};
+    const cuuint32_t box[2] = {(cuuint32_t)kD, (cuuint32_t)kTileRows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)dict, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("ebsd_topk: cuTensorMapEncodeTiled failed with %d", (int)cr);
+        return EBSD_ERR_CUDA;
+    }
+
+    TopkParams p;
+    p.queries = queries;
+    p.Q = Q;
+    p.N = N;
+    p.index_base = index_base;
+    p.k = k;
+    p.n_qtiles = pl.n_qtiles;
+    p.n_splits = pl.n_splits;
+    p.tiles_per_split = pl.tiles_per_split;
+    p.parts = (Entry *)workspace;
+    p.out_dot = out_dot;
+    p.out_idx = (long long *)out_idx;
+    p.out_dist = out_dist;
+    rc = pl.tq == 8 ? launch_topk<8>(map, p, sms, st) : launch_topk<1>(map, p, sms, st);
+    if (rc) return rc;
+    if (pl.n_splits > 1) {
+        const int wpb = 8;
+        topk_merge_parts_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+            p.parts, pl.n_splits, Q, k, index_base, out_dot, (long long *)out_idx, out_dist);
+        EBSD_CUDA_TRY(cudaGetLastError());
+    }
+    return EBSD_OK;
+}
+
+int ebsd_topk_merge(const float *dots, const int64_t *idx, int R, int64_t Q, int k, float *out_dot,
+                    int64_t *out_idx, float *out_dist, void *stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    EBSD_REQUIRE(k >= 1 && k <= EBSD_MAX_TOPK, "ebsd_topk_merge: k must be in [1,%d], got %d", EBSD_MAX_TOPK, k);
+    EBSD_REQUIRE(R >= 0 && Q >= 0, "ebsd_topk_merge: negative size");
+    if (Q == 0) return EBSD_OK;
+    EBSD_REQUIRE(out_dot && out_idx && (R == 0 || (dots && idx)), "ebsd_topk_merge: null pointer");
+    const int wpb = 8;
+    topk_merge_global_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        dots, (const long long *)idx, R, Q, k, out_dot, (long long *)out_idx, out_dist);
+    EBSD_CUDA_TRY(cudaGetLastError());
+    return EBSD_OK;
+}
+
+}  // extern "C"

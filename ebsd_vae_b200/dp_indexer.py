@@ -1,0 +1,180 @@
+"""``DiffractionPatternIndexer`` / ``IndexerConfig`` with the reference's API (latice/index/dp_indexer.py:27-297).
+
+encode -> store -> query -> consensus, with every stage on the GPU:
+
+* patterns are quantised/cropped on the host exactly like the reference transform (ebsd_vae_b200/transform.py),
+  shipped as uint8 and encoded by the native encoder (only ``mu`` is computed; the reference runs the whole
+  VAE and discards everything else, dp_indexer.py:136,183,284);
+* latents never leave the device between encoder, dictionary and search when the caller stays inside
+  ``build_dictionary`` / ``index_patterns_batch``.
+"""
+from __future__ import annotations
+
+import logging
+from pathlib import Path
+from typing import Literal
+
+import numpy as np
+import torch
+from numpy.typing import NDArray
+from pydantic.dataclasses import dataclass
+
+from .model import EncoderEngine
+from .transform import load_patterns, parse_rotation_angles, quantise_u8, transform_batch_u8, _axis_window
+from .vector_db import LatentVectorDatabase, LatentVectorDatabaseConfig, OrientationResult
+
+logger = logging.getLogger(__name__)
+
+
+@dataclass
+class IndexerConfig:
+    """Configuration for the diffraction pattern indexer (fields/defaults of dp_indexer.py:26-48).
+
+    ``pattern_path`` / ``angles_path`` are only needed by ``build_dictionary`` and default to None here (the
+    reference declares them required but then constructs ``IndexerConfig()`` without them, dp_indexer.py:72).
+    ``device`` defaults to "cuda": this implementation has no CPU path.
+    """
+
+    pattern_path: Path | None = None
+    angles_path: Path | None = None
+    batch_size: int = 64
+    device: Literal["cuda", "cpu", "mps"] = "cuda"
+    latent_dim: int = 16
+    random_seed: int = 42
+    image_size: tuple[int, int] = (128, 128)
+    top_n: int = 20
+    orientation_threshold: float = 3.0
+
+
+class DiffractionPatternIndexer:
+    """Indexes diffraction patterns using the VAE encoder and the GPU latent dictionary."""
+
+    #: patterns encoded per native call inside build_dictionary / encode_patterns_batch (host staging granularity)
+    ENCODE_CHUNK = 4096
+
+    def __init__(self, model, db: LatentVectorDatabase | None = None, config: IndexerConfig | None = None) -> None:
+        self.config = config if config is not None else IndexerConfig()
+        self.db = db if db is not None else LatentVectorDatabase(
+            LatentVectorDatabaseConfig(dimension=self.config.latent_dim)
+        )
+        np.random.seed(self.config.random_seed)
+        torch.manual_seed(self.config.random_seed)
+
+        if self.config.device != "cuda":
+            raise RuntimeError(
+                f"device={self.config.device!r}: ebsd_vae_b200 runs on CUDA (sm_100a) only and has no CPU fallback"
+            )
+        if not torch.cuda.is_available():
+            raise RuntimeError("CUDA is not available; ebsd_vae_b200 has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        logger.info(f"Using device: {self.device}")
+
+        self.model = model
+        self.model.eval()
+        self.model.to(self.device)
+        self._engine: EncoderEngine | None = None
+
+    # ------------------------------------------------------------------ encoder plumbing
+    @property
+    def engine(self) -> EncoderEngine:
+        if self._engine is None:
+            if hasattr(self.model, "engine") and callable(self.model.engine):
+                self._engine = self.model.engine()
+            else:  # e.g. the reference's own nn.Module: take its weights
+                self._engine = EncoderEngine(self.model.state_dict(), self.device)
+        return self._engine
+
+    def _encode_u8_host(self, u8: np.ndarray) -> torch.Tensor:
+        """uint8 [B,128,128] on the host -> mu [B,16] on the device (pinned staging, chunked)."""
+        outs = []
+        for a in range(0, len(u8), self.ENCODE_CHUNK):
+            chunk = torch.from_numpy(u8[a : a + self.ENCODE_CHUNK])
+            dev = chunk.pin_memory().to(self.device, non_blocking=True)
+            outs.append(self.engine.encode(dev))
+        if not outs:
+            return torch.empty((0, self.config.latent_dim), dtype=torch.float32, device=self.device)
+        return outs[0] if len(outs) == 1 else torch.cat(outs)
+
+    def _encode_any(self, patterns) -> torch.Tensor:
+        """Reference input rules (dp_indexer.py:124-131, 150-169): ndarrays go through the transform, tensors bypass it."""
+        if isinstance(patterns, np.ndarray):
+            if patterns.ndim not in (2, 3):
+                raise AssertionError(f"Expected 4D tensor, got {patterns.ndim + 1}D")
+            return self._encode_u8_host(transform_batch_u8(patterns, tuple(self.config.image_size)))
+        t = patterns
+        if t.dim() == 2:
+            t = t[None]
+        elif t.dim() == 4:
+            if t.shape[1] != 1:
+                raise ValueError(f"expected a single channel, got {t.shape[1]}")
+            t = t[:, 0]
+        elif t.dim() != 3:
+            raise AssertionError(f"Expected 4D tensor, got {t.dim()}D")
+        t = t.to(self.device)
+        if t.dtype != torch.uint8:
+            t = t.to(torch.float32)
+        outs = [self.engine.encode(t[a : a + self.ENCODE_CHUNK]) for a in range(0, t.shape[0], self.ENCODE_CHUNK)]
+        return outs[0] if len(outs) == 1 else torch.cat(outs)
+
+    # ------------------------------------------------------------------ reference API
+    def build_dictionary(self) -> None:
+        """Generate latent vectors from ``config.pattern_path`` / ``config.angles_path`` and add them to the db."""
+        if self.config.pattern_path is None or self.config.angles_path is None:
+            raise ValueError("IndexerConfig.pattern_path and angles_path are required by build_dictionary")
+        logger.info(f"Generating latent vectors from patterns in {self.config.pattern_path}")
+        latent_vectors, orientations = self._extract_latent_vectors_with_angles(
+            self.config.pattern_path, self.config.angles_path
+        )
+        logger.info(f"Adding {len(latent_vectors)} vectors to database")
+        self.db.add_vectors(latent_vectors, orientations)
+
+    def _extract_latent_vectors_with_angles(self, pattern_path, angles_path):
+        """Encode every pattern of the .npy file; returns (latents CUDA [N,16] f32, orientations [N,3] f64).
+
+        The reference's dataset casts each pattern to float64 before the transform (data_module.py:132), so
+        integer-typed files are scaled by 255 and wrap modulo 256 -- reproduced here.
+        """
+        data = load_patterns(pattern_path)
+        angles = parse_rotation_angles(angles_path)
+        if len(angles) < len(data):
+            raise ValueError(f"angle file has {len(angles)} rows for {len(data)} patterns")
+        th, tw = tuple(self.config.image_size)
+        sy, dy, ly = _axis_window(data.shape[1], th)
+        sx, dx, lx = _axis_window(data.shape[2], tw)
+        outs = []
+        for a in range(0, len(data), self.ENCODE_CHUNK):
+            window = np.asarray(data[a : a + self.ENCODE_CHUNK, sy : sy + ly, sx : sx + lx]).astype(np.float64)
+            q = quantise_u8(window)
+            if (ly, lx) != (th, tw):
+                full = np.zeros((len(q), th, tw), dtype=np.uint8)
+                full[:, dy : dy + ly, dx : dx + lx] = q
+                q = full
+            outs.append(self._encode_u8_host(np.ascontiguousarray(q)))
+        latents = torch.cat(outs) if outs else torch.empty((0, 16), dtype=torch.float32, device=self.device)
+        return latents, angles[: len(data)]
+
+    def encode_pattern(self, pattern) -> NDArray[np.float32]:
+        """Encode a single diffraction pattern to latent space -> (16,) float32."""
+        return self._encode_any(pattern).cpu().numpy().squeeze()
+
+    def encode_patterns_batch(self, patterns) -> NDArray[np.float32]:
+        """Encode multiple diffraction patterns [B,H,W] -> (B,16) float32."""
+        return self._encode_any(patterns).cpu().numpy()
+
+    def index_pattern(self, pattern, top_n: int | None = None,
+                      orientation_threshold: float | None = None) -> OrientationResult:
+        """Index a diffraction pattern and return the best orientation (dp_indexer.py:188-214)."""
+        top_n = top_n or self.config.top_n
+        orientation_threshold = orientation_threshold or self.config.orientation_threshold
+        latent_vector = self.encode_pattern(pattern)
+        return self.db.find_best_orientation(
+            latent_vector, top_n=top_n, orientation_threshold=orientation_threshold
+        )
+
+    def index_patterns_batch(self, patterns, **kwargs):
+        """Index multiple patterns; ``kwargs`` go to ``find_best_orientation`` (dp_indexer.py:216-232).
+
+        Latents stay on the device between the encoder and the search.
+        """
+        latent_vectors = self._encode_any(patterns)
+        return self.db.find_best_orientations_batch(latent_vectors, batch_size=self.config.batch_size, **kwargs)

@@ -1,0 +1,80 @@
+"""Host-side input contract of the indexing path: 8-bit quantise + centre-crop, angle-file parsing.
+
+Mirrors ``create_default_transform`` (latice/data_module.py:17-33 = ToPILImage -> Grayscale ->
+CenterCrop -> ToTensor) and ``DPdataset._parse_rotation_angles`` (latice/data_module.py:87-116),
+vectorised over the batch.  The encoder consumes the uint8 image directly: ToTensor's ``k / 255`` is
+applied inside the first convolution kernel, so 16 KiB per pattern cross PCIe instead of 64 KiB.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+
+
+def _axis_window(size: int, target: int) -> tuple[int, int, int]:
+    """(source start, destination start, length) of the copy along one axis (torchvision center_crop)."""
+    if size >= target:
+        start = int(round((size - target) / 2.0))  # Python round: half to even, like the reference
+        return start, 0, target
+    return 0, (target - size) // 2, size
+
+
+def quantise_u8(patterns: np.ndarray) -> np.ndarray:
+    """``(x * 255).astype(uint8)`` for float input (torchvision to_pil_image), identity for uint8."""
+    if np.issubdtype(patterns.dtype, np.floating):
+        return (patterns * 255).astype(np.uint8)
+    if patterns.dtype == np.uint8:
+        return patterns
+    raise TypeError(f"Input type {patterns.dtype} is not supported")  # ToPILImage rejects other dtypes
+
+
+def transform_batch_u8(patterns: np.ndarray, image_size: tuple[int, int] = (128, 128)) -> np.ndarray:
+    """[B,H,W] or [H,W] patterns -> contiguous uint8 [B,th,tw]; value k stands for k/255."""
+    if patterns.ndim == 2:
+        patterns = patterns[None]
+    if patterns.ndim != 3:
+        raise ValueError(f"pic should be 2/3 dimensional. Got {patterns.ndim} dimensions.")
+    th, tw = image_size
+    _, h, w = patterns.shape
+    sy, dy, ly = _axis_window(h, th)
+    sx, dx, lx = _axis_window(w, tw)
+    window = patterns[:, sy : sy + ly, sx : sx + lx]
+    if (ly, lx) == (th, tw):
+        return np.ascontiguousarray(quantise_u8(window))
+    out = np.zeros((patterns.shape[0], th, tw), dtype=np.uint8)
+    out[:, dy : dy + ly, dx : dx + lx] = quantise_u8(window)
+    return out
+
+
+def parse_rotation_angles(path: str | Path) -> np.ndarray:
+    """Angle file -> float64 [N,3] (z1, x, z2 = phi1, Phi, phi2 in degrees).
+
+    Two header lines are skipped; fields are separated by single spaces (empty fields dropped), as in
+    latice/data_module.py:100-110.  Errors follow the reference: FileNotFoundError is re-raised,
+    anything else becomes ``ValueError("Failed to parse rotation angles file: ...")``.
+    """
+    path = Path(path)
+    try:
+        with open(path) as fh:
+            lines = fh.readlines()[2:]
+        rows = [[tok for tok in line.strip().split(" ") if tok] for line in lines]
+        if any(len(r) != 3 for r in rows):
+            bad = next(len(r) for r in rows if len(r) != 3)
+            raise ValueError(f"3 columns passed, passed data had {bad} columns")
+        return np.array(rows, dtype=np.float64).reshape(-1, 3)
+    except FileNotFoundError:
+        raise
+    except Exception as exc:  # noqa: BLE001 - mirrors the reference's catch-all
+        raise ValueError(f"Failed to parse rotation angles file: {exc}") from exc
+
+
+def load_patterns(path: str | Path) -> np.ndarray:
+    """``np.load`` with the reference's checks (latice/data_module.py:69-78)."""
+    try:
+        data = np.load(Path(path), mmap_mode="r")
+    except Exception as exc:  # noqa: BLE001
+        raise ValueError("Only .npy data files are supported.") from exc
+    if data.ndim != 3:
+        raise ValueError("The input dataset should be 3D.")
+    return data

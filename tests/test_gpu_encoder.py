@@ -1,0 +1,81 @@
+"""GPU parity: the native encoder against the torch-fp32 oracle (oracle/encoder_ref.py) and the golden vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import encoder_ref as R
+
+pytestmark = pytest.mark.gpu
+
+LATENT_REL_TOL = 1e-3  # BASELINE.json north_star: "Latents must match torch within 1e-3 relative"
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)
+
+
+@pytest.fixture(scope="module")
+def engine42():
+    import ebsd_vae_b200 as E
+    return E.EncoderEngine(R.make_state_dict(42), "cuda"), R.make_state_dict(42)
+
+
+def test_golden_latents(engine42, golden_dir):
+    eng, _ = engine42
+    g = np.load(os.path.join(golden_dir, "encoder_seed42.npz"))
+    mu, logvar = eng.encode(torch.from_numpy(g["patterns"]).cuda(), want_logvar=True)
+    rel_mu, rel_lv = _rel(mu.cpu().numpy(), g["mu"]), _rel(logvar.cpu().numpy(), g["logvar"])
+    print("golden rel err mu", rel_mu.max(), "logvar", rel_lv.max())
+    assert rel_mu.max() < LATENT_REL_TOL and rel_lv.max() < LATENT_REL_TOL
+
+
+@pytest.mark.parametrize("batch", [1, 3, 32, 33, 70])
+def test_batches_match_oracle(engine42, batch):
+    eng, sd = engine42
+    p = R.synthetic_patterns(batch, seed=100 + batch)
+    mu = eng.encode(p.cuda()).cpu().numpy()
+    want, _ = R.encode(sd, R.u8_to_input(p))
+    rel = _rel(mu, want.numpy())
+    print(f"batch {batch}: max rel {rel.max():.3e} median {np.median(rel):.3e}")
+    assert rel.max() < LATENT_REL_TOL
+
+
+def test_float_input_path_and_other_seed():
+    import ebsd_vae_b200 as E
+    sd = R.make_state_dict(7)
+    eng = E.EncoderEngine(sd, "cuda")
+    x = torch.rand((5, 128, 128), generator=torch.Generator().manual_seed(1))  # tensors bypass the 8-bit transform
+    mu = eng.encode(x.cuda()).cpu().numpy()
+    want, _ = R.encode(sd, x.unsqueeze(1))
+    assert _rel(mu, want.numpy()).max() < LATENT_REL_TOL
+
+
+def test_extreme_patterns(engine42):
+    eng, sd = engine42
+    p = torch.zeros((4, 128, 128), dtype=torch.uint8)
+    p[1] = 255
+    p[2, 64, 64] = 255                      # a single hot pixel: large InstanceNorm dynamic range
+    p[3] = (torch.arange(128 * 128) % 2 * 255).reshape(128, 128).to(torch.uint8)
+    mu = eng.encode(p.cuda()).cpu().numpy()
+    want, _ = R.encode(sd, R.u8_to_input(p))
+    want = want.numpy()
+    assert np.isfinite(mu).all()
+    err = np.linalg.norm(mu - want, axis=1) / np.maximum(np.linalg.norm(want, axis=1), 1e-3)
+    print("extreme rel", err)
+    assert err.max() < 5e-3  # constant planes are 0/0-like after InstanceNorm: looser bound, finite is the point
+
+
+def test_module_forward_returns_reference_tuple(engine42):
+    import ebsd_vae_b200 as E
+    _, sd = engine42
+    m = E.VariationalAutoEncoderRawData()
+    m.load_state_dict(sd)
+    m.eval().to("cuda")
+    p = R.synthetic_patterns(2, seed=5)
+    z, x_hat, mu, std = m(R.u8_to_input(p).cuda())
+    want_mu, want_lv = R.encode(sd, R.u8_to_input(p))
+    assert _rel(mu.cpu().numpy(), want_mu.numpy()).max() < LATENT_REL_TOL
+    np.testing.assert_allclose(std.cpu().numpy(), torch.exp(want_lv / 2).numpy(), rtol=2e-3)

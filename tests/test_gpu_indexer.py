@@ -1,0 +1,129 @@
+"""GPU end-to-end: DiffractionPatternIndexer.build_dictionary / index_pattern against the oracle pipeline
+(transform -> encoder -> exact top-k -> consensus) on the reference's sample-shaped inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import consensus_ref as C
+from oracle import encoder_ref as R
+from oracle import topk_ref as T
+from oracle import transform_ref as X
+
+pytestmark = pytest.mark.gpu
+N_PAT = 96
+
+
+def _misorientation_deg(e1, e2):
+    q1, q2 = C.quat_from_euler_zxz_deg(e1), C.quat_from_euler_zxz_deg(e2)
+    return np.degrees(C.quat_angle(C.quat_mul(q1, C.quat_conj(q2))))
+
+
+@pytest.fixture(scope="module")
+def setup(tmp_path_factory, golden_dir):
+    import ebsd_vae_b200 as E
+    tmp = tmp_path_factory.mktemp("sample")
+    base = R.synthetic_patterns(N_PAT, seed=99, size=144).numpy().astype(np.float64) / 255.0
+    patterns = base[:, :140, :]  # (N, 140, 144): exercises the centre crop
+    np.save(tmp / "sample_pattern.npy", patterns)
+    sd = R.make_state_dict(42)
+    torch.save(sd, tmp / "vae-best.pt")
+    model = E.VariationalAutoEncoderRawData()
+    model.load_state_dict(torch.load(tmp / "vae-best.pt", weights_only=True))
+    cfg = E.IndexerConfig(pattern_path=tmp / "sample_pattern.npy",
+                          angles_path=os.path.join(golden_dir, "anglefile_sample.txt"), device="cuda", top_n=10)
+    indexer = E.DiffractionPatternIndexer(model, config=cfg)
+    indexer.build_dictionary()
+    # oracle pipeline
+    u8 = np.stack([X.transform_u8(p) for p in patterns])
+    mu, _ = R.encode(sd, R.u8_to_input(torch.from_numpy(u8)))
+    angles = X.parse_rotation_angles(os.path.join(golden_dir, "anglefile_sample.txt"))[:N_PAT]
+    return indexer, patterns, u8, mu.numpy(), angles, sd
+
+
+def test_dictionary_contents(setup):
+    indexer, patterns, u8, mu, angles, _ = setup
+    db = indexer.db
+    assert db.get_count() == N_PAT
+    lat = db._latents[:N_PAT].cpu().numpy()
+    want = T.normalize_rows(mu)
+    rel = np.linalg.norm(lat - want, axis=1)
+    assert rel.max() < 1e-3
+    np.testing.assert_array_equal(db._eulers[:N_PAT].cpu().numpy(), angles)
+
+
+def test_encode_apis_match_oracle(setup):
+    indexer, patterns, u8, mu, _, _ = setup
+    one = indexer.encode_pattern(patterns[3])
+    assert isinstance(one, np.ndarray) and one.shape == (16,) and one.dtype == np.float32
+    many = indexer.encode_patterns_batch(patterns[:10])
+    assert many.shape == (10, 16)
+    rel = np.linalg.norm(many - mu[:10], axis=1) / np.linalg.norm(mu[:10], axis=1)
+    assert rel.max() < 1e-3
+    np.testing.assert_allclose(one, many[3], rtol=0, atol=1e-6)
+    t = indexer.encode_pattern(torch.from_numpy(u8[3].astype(np.float32) / 255.0))  # tensors bypass the transform
+    np.testing.assert_allclose(t, one, rtol=0, atol=1e-5)
+
+
+def test_index_pattern_reference_defaults(setup):
+    indexer, patterns, u8, mu, angles, _ = setup
+    res = indexer.index_pattern(patterns[5])
+    # top_n=10 < min_required_matches=18 (chroma_db.py:266): the reference always fails here
+    assert res.success is False and res.mean_orientation is None
+    assert res.candidate_orientations.shape == (10, 3) and res.distances.shape == (10,)
+    odot, oidx = T.topk(T.normalize_rows(mu), T.normalize_rows(mu[5:6]), 10)
+    np.testing.assert_array_equal(res.candidate_orientations[0], angles[oidx[0, 0]])
+    np.testing.assert_array_equal(res.best_orientation, angles[5])  # a dictionary pattern finds itself
+    assert len(set(map(tuple, res.candidate_orientations)) & set(map(tuple, angles[oidx[0]]))) >= 9
+    np.testing.assert_allclose(res.distances, 1.0 - odot[0], atol=2e-3)
+    assert list(res.similar_indices) == list(range(10))  # radian threshold 3.0 lets every candidate through
+
+
+def test_search_on_reference_latents_is_bit_exact(setup):
+    """North star: top-k indices on the REFERENCE's latents match exact brute force bit-exactly."""
+    import ebsd_vae_b200 as E
+    _, _, _, mu, angles, _ = setup
+    db = E.LatentVectorDatabase()
+    db.add_vectors(mu, angles)
+    batch = db.find_best_orientations_batch(mu, top_n=10, min_required_matches=3, orientation_threshold=0.2)
+    odot, oidx = T.topk(T.normalize_rows(mu), T.normalize_rows(mu), 10)
+    np.testing.assert_array_equal(batch.indices, oidx)
+    np.testing.assert_array_equal(batch.distances, np.float32(1.0) - odot)
+
+
+def test_batch_indexing_consensus_matches_oracle(setup):
+    indexer, patterns, _, _, _, _ = setup
+    results = indexer.index_patterns_batch(patterns[:40], top_n=10, min_required_matches=3,
+                                           orientation_threshold=0.2)
+    assert len(results) == 40
+    n_ok = 0
+    for r in results:
+        want = C.find_best_orientation(r.candidate_orientations, 0.2, 3, 3, mode="chroma")
+        assert r.success == want.success
+        np.testing.assert_array_equal(r.similar_indices, want.similar_indices)
+        if r.success:
+            n_ok += 1
+            assert _misorientation_deg(r.mean_orientation, want.mean_orientation) < 0.1
+        else:
+            assert r.mean_orientation is None
+        np.testing.assert_array_equal(r.best_orientation, r.candidate_orientations[0])
+    assert n_ok > 0
+
+
+def test_uint8_file_goes_through_float64_cast_like_the_reference(tmp_path, golden_dir, setup):
+    """DPdataset casts to float64 before ToPILImage (data_module.py:132): uint8 files wrap to (-v) mod 256."""
+    import ebsd_vae_b200 as E
+    _, _, _, _, _, sd = setup
+    raw = R.synthetic_patterns(4, seed=5).numpy()
+    np.save(tmp_path / "u8.npy", raw)
+    model = E.VariationalAutoEncoderRawData()
+    model.load_state_dict(sd)
+    cfg = E.IndexerConfig(pattern_path=tmp_path / "u8.npy",
+                          angles_path=os.path.join(golden_dir, "anglefile_sample.txt"), device="cuda")
+    idx = E.DiffractionPatternIndexer(model, config=cfg)
+    idx.build_dictionary()
+    u8 = np.stack([X.transform_u8(p.astype(np.float64)) for p in raw])
+    mu, _ = R.encode(sd, R.u8_to_input(torch.from_numpy(u8)))
+    lat = idx.db._latents[:4].cpu().numpy()
+    assert np.linalg.norm(lat - T.normalize_rows(mu.numpy()), axis=1).max() < 1e-3

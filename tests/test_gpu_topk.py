@@ -1,0 +1,140 @@
+"""GPU parity: ebsd_normalize_rows / ebsd_topk / ebsd_topk_merge against the canonical-fp32 C oracle (bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import topk_ref as T
+
+pytestmark = pytest.mark.gpu
+
+
+def _db(latents, index_base=0):
+    import ebsd_vae_b200 as E
+    db = E.LatentVectorDatabase()
+    db.index_base = index_base
+    if len(latents):
+        db.add_vectors(latents, np.zeros((len(latents), 3)))
+    return db
+
+
+def _data(n, q, seed, dup=0.0):
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(n, 16)).astype(np.float32)
+    nd = int(n * dup)
+    if nd:
+        d[rng.integers(0, n, size=nd)] = d[rng.integers(0, n, size=nd)]
+    qs = d[rng.integers(0, max(n, 1), size=q)] if n else rng.normal(size=(q, 16))
+    qs = (qs + 0.05 * rng.normal(size=(q, 16))).astype(np.float32)
+    return d, qs
+
+
+def _search(db, q, k):
+    qh = db._prepare_queries(q)
+    dot, idx, dist = db.search_device(qh, k)
+    torch.cuda.synchronize()
+    return qh.cpu().numpy(), dot.cpu().numpy(), idx.cpu().numpy(), dist.cpu().numpy()
+
+
+def test_normalize_rows_bit_exact():
+    d, _ = _data(10000, 1, 0)
+    d[17] = 0.0
+    d[18] *= 1e-20
+    db = _db(d)
+    got = db._latents[: db.get_count()].cpu().numpy()
+    np.testing.assert_array_equal(got, T.normalize_rows(d))
+
+
+@pytest.mark.parametrize("n,q,k,dup", [
+    (625, 1, 10, 0.0), (625, 1, 20, 0.0), (1000, 5, 20, 0.01), (5000, 200, 10, 0.01), (127, 3, 10, 0.0),
+    (128, 16, 10, 0.0), (129, 17, 32, 0.0), (7, 4, 10, 0.0), (100_000, 300, 10, 0.001), (33_333, 1000, 1, 0.01),
+    (20_000, 129, 10, 0.3),
+])
+def test_topk_bit_exact_vs_oracle(n, q, k, dup):
+    d, qs = _data(n, q, seed=n + q + k, dup=dup)
+    db = _db(d, index_base=1000)
+    qh, dot, idx, dist = _search(db, qs, k)
+    dn = db._latents[:n].cpu().numpy()
+    np.testing.assert_array_equal(qh, T.normalize_rows(qs))
+    odot, oidx = T.topk(dn, qh, k, index_base=1000, nthreads=8)
+    np.testing.assert_array_equal(idx, oidx)
+    np.testing.assert_array_equal(dot, odot)
+    filled = oidx >= 0
+    np.testing.assert_array_equal(dist[filled], (np.float32(1.0) - odot)[filled])
+
+
+def test_exact_duplicates_tie_break_on_index():
+    d, qs = _data(4096, 8, 3)
+    d[1000:1012] = d[5]
+    qs[0] = d[5]
+    db = _db(d)
+    _, dot, idx, _ = _search(db, qs, 10)
+    assert idx[0, 0] == 5 and list(idx[0, 1:]) == list(range(1000, 1009))
+
+
+def test_empty_dictionary_and_empty_queries():
+    db = _db(np.zeros((0, 16), np.float32))
+    _, dot, idx, _ = _search(db, np.ones((3, 16), np.float32), 10)
+    assert (idx == -1).all() and np.isneginf(dot).all()
+    d, _ = _data(300, 1, 1)
+    db = _db(d)
+    _, dot, idx, _ = _search(db, np.zeros((0, 16), np.float32), 10)
+    assert idx.shape == (0, 10)
+
+
+def test_merge_kernel_matches_oracle_and_sharded_equals_whole():
+    from ebsd_vae_b200 import _native
+    d, qs = _data(30_011, 257, 9, dup=0.01)
+    whole = _db(d)
+    qh, dot, idx, _ = _search(whole, qs, 10)
+    cuts = [0, 10_000, 10_001, 25_000, 30_011]
+    dn = whole._latents[: len(d)]
+    dots, idxs = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        shard = _db(np.zeros((0, 16), np.float32), index_base=a)
+        shard._latents, shard._count, shard._capacity = dn[a:b].clone(), b - a, b - a
+        qd = torch.from_numpy(qh).cuda()
+        sd, si, _ = shard.search_device(qd, 10)
+        dots.append(sd)
+        idxs.append(si)
+    dots_t, idx_t = torch.stack(dots).contiguous(), torch.stack(idxs).contiguous()
+    out_d = torch.empty_like(dots[0])
+    out_i = torch.empty_like(idxs[0])
+    out_dist = torch.empty_like(dots[0])
+    lib = _native.load()
+    _native.check(lib.ebsd_topk_merge(dots_t.data_ptr(), idx_t.data_ptr(), 4, 257, 10, out_d.data_ptr(),
+                                      out_i.data_ptr(), out_dist.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream), "merge")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out_i.cpu().numpy(), idx)
+    np.testing.assert_array_equal(out_d.cpu().numpy(), dot)
+    od, oi = T.topk_merge(dots_t.cpu().numpy(), idx_t.cpu().numpy())
+    np.testing.assert_array_equal(oi, idx)
+    np.testing.assert_array_equal(od, dot)
+
+
+def test_full_size_properties_1m_rows():
+    """BASELINE config 3 size (N = 1M): sortedness, split-invariance, and a sampled bit-exact check."""
+    g = torch.Generator(device="cuda").manual_seed(2024)
+    d = torch.randn((1_000_000, 16), generator=g, device="cuda")
+    d[::1000] = d[1::1000]  # 0.1 % exact duplicates
+    import ebsd_vae_b200 as E
+    db = E.LatentVectorDatabase()
+    db.add_vectors(d, torch.zeros((len(d), 3), dtype=torch.float64, device="cuda"))
+    q = d[torch.randint(0, len(d), (4096,), generator=g, device="cuda")] + 0.05 * torch.randn(
+        (4096, 16), generator=g, device="cuda")
+    qh = db._prepare_queries(q)
+    dot, idx, _ = db.search_device(qh, 10)
+    assert bool((dot[:, 1:] <= dot[:, :-1]).all())
+    ties = dot[:, 1:] == dot[:, :-1]
+    assert bool((idx[:, 1:][ties] > idx[:, :-1][ties]).all())
+    assert int(ties.sum()) > 0
+    # a different query batch size takes a different (query tile, split) plan: results must not change
+    dot2, idx2, _ = db.search_device(qh[:100].contiguous(), 10)
+    assert torch.equal(idx2, idx[:100]) and torch.equal(dot2, dot[:100])
+    dot3, idx3, _ = db.search_device(qh[:7].contiguous(), 10)
+    assert torch.equal(idx3, idx[:7]) and torch.equal(dot3, dot[:7])
+    # sampled oracle check
+    dn = db._latents[: len(d)].cpu().numpy()
+    odot, oidx = T.topk(dn, qh[:48].cpu().numpy(), 10, nthreads=8)
+    np.testing.assert_array_equal(idx[:48].cpu().numpy(), oidx)
+    np.testing.assert_array_equal(dot[:48].cpu().numpy(), odot)

@@ -1,0 +1,119 @@
+"""CPU-side tests: host logic of the drop-in API and the C-ABI surface (no GPU compute)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import ebsd_vae_b200 as E
+from ebsd_vae_b200 import _native, transform
+from oracle import transform_ref
+from oracle.make_golden import TRANSFORM_CASES, transform_input
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ebsd_b200.h")).read()
+    declared = set(re.findall(r"\b(ebsd_[a-z0-9_]+)\s*\(", header))
+    declared -= {"ebsd_encoder"}
+    assert declared == set(_native.SYMBOLS), declared ^ set(_native.SYMBOLS)
+    lib = _native.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.ebsd_abi_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour on a box without a GPU")
+def test_calls_fail_loudly_without_a_gpu():
+    lib = _native.load()
+    rc = lib.ebsd_normalize_rows(None, 0, 16, None)
+    assert rc != 0 and "CUDA" in _native.last_error()
+    with pytest.raises(RuntimeError):
+        E.LatentVectorDatabase().add_vectors(np.zeros((2, 16), np.float32), np.zeros((2, 3)))
+    with pytest.raises(RuntimeError):
+        E.DiffractionPatternIndexer(E.VariationalAutoEncoderRawData())
+    with pytest.raises(RuntimeError):
+        E.EncoderEngine(E.VariationalAutoEncoderRawData().state_dict(), "cpu")
+
+
+def test_transform_matches_golden_and_oracle(golden_dir):
+    g = np.load(os.path.join(golden_dir, "transform.npz"))
+    for case, want in zip(TRANSFORM_CASES, g["outputs"]):
+        x = transform_input(*case)
+        got = transform.transform_batch_u8(x, (128, 128))
+        assert got.shape == (1, 128, 128) and got.dtype == np.uint8
+        np.testing.assert_array_equal(got[0], want, err_msg=str(case))
+        np.testing.assert_array_equal(got[0], transform_ref.transform_u8(x, (128, 128)))
+
+
+def test_transform_batch_and_bad_dtype():
+    rng = np.random.default_rng(5)
+    x = rng.random((6, 131, 140))
+    got = transform.transform_batch_u8(x)
+    for i in range(6):
+        np.testing.assert_array_equal(got[i], transform_ref.transform_u8(x[i]))
+    with pytest.raises(TypeError):
+        transform.transform_batch_u8(np.zeros((2, 128, 128), dtype=np.int64))
+
+
+def test_angle_parser(golden_dir, tmp_path):
+    got = transform.parse_rotation_angles(os.path.join(golden_dir, "anglefile_sample.txt"))
+    np.testing.assert_array_equal(got, np.load(os.path.join(golden_dir, "angles_sample.npy")))
+    with pytest.raises(FileNotFoundError):
+        transform.parse_rotation_angles(tmp_path / "missing.txt")
+    bad = tmp_path / "bad.txt"
+    bad.write_text("eu\n2\n0 1 0\n0 1\n")
+    with pytest.raises(ValueError, match="Failed to parse rotation angles file"):
+        transform.parse_rotation_angles(bad)
+
+
+def test_config_defaults_match_reference():
+    c = E.IndexerConfig()
+    assert (c.batch_size, c.latent_dim, c.random_seed, tuple(c.image_size), c.top_n, c.orientation_threshold) == (
+        64, 16, 42, (128, 128), 20, 3.0)
+    d = E.LatentVectorDatabaseConfig()
+    assert (d.collection_name, d.persist_directory, d.dimension) == ("latent_vectors", ".chroma_db", 16)
+    assert E.ChromaLatentVectorDatabase is E.LatentVectorDatabase
+
+
+def test_db_validation_messages():
+    db = E.LatentVectorDatabase()
+    assert db.get_count() == 0 and db.collection_name == "latent_vectors" and db.dimension == 16
+    with pytest.raises(ValueError, match="Number of latent vectors and orientations must match"):
+        db.add_vectors(np.zeros((3, 16)), np.zeros((2, 3)))
+    with pytest.raises(ValueError, match="Expected latent vectors of dimension 16, got 8"):
+        db.add_vectors(np.zeros((3, 8)), np.zeros((3, 3)))
+    with pytest.raises(ValueError, match="Expected query vector of dimension 16, got 8"):
+        db.query_similar(np.zeros(8))
+    with pytest.raises(ValueError, match="Expected query vector of dimension"):
+        db.find_best_orientation(np.zeros(8))
+
+
+def test_orientation_result_top_n():
+    rng = np.random.default_rng(0)
+    cand = rng.random((5, 3)) * 360
+    r = E.OrientationResult(query_vector=rng.random(16), best_orientation=cand[0], candidate_orientations=cand,
+                            distances=np.array([0.5, 0.1, 0.3, 0.2, 0.4]))
+    np.testing.assert_array_equal(r.get_top_n_orientations(3), cand[[1, 3, 2]])
+    assert r.get_top_n_orientations(10).shape == (5, 3)
+    r.distances = None
+    np.testing.assert_array_equal(r.get_top_n_orientations(2), cand[:2])
+
+
+def test_weight_extraction_accepts_reference_layouts():
+    from oracle import encoder_ref
+    sd = encoder_ref.make_state_dict(3)
+    full = dict(sd)
+    full["decoder.1.0.weight"] = torch.zeros(1)  # extra keys of the full VAE are ignored
+    hot = E.model.extract_hot_state_dict(full)
+    assert list(hot) == list(E.model.HOT_KEYS)
+    lightning = {"state_dict": {"model." + k: v for k, v in sd.items()}}
+    assert torch.equal(E.model.extract_hot_state_dict(lightning)["mu.0.bias"], sd["mu.0.bias"])
+    m = E.VariationalAutoEncoderRawData()
+    m.load_state_dict(full)
+    assert torch.equal(m.state_dict()["encoder.13.0.weight"], sd["encoder.13.0.weight"])
+    with pytest.raises(KeyError):
+        E.model.extract_hot_state_dict({"foo": torch.zeros(1)})
