@@ -40,6 +40,7 @@ class EbsdWeights(ctypes.Structure):
 SYMBOLS = {
     "ebsd_abi_version": (_int, []),
     "ebsd_last_error": (ctypes.c_char_p, []),
+    "ebsd_launch_count": (ctypes.c_uint64, []),
     "ebsd_encoder_create": (_int, [ctypes.POINTER(_c_void_p), ctypes.POINTER(EbsdWeights), _int, _c_void_p]),
     "ebsd_encoder_destroy": (None, [_c_void_p]),
     "ebsd_encoder_workspace_bytes": (_size_t, [_c_void_p, _i64]),

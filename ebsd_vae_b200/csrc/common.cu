@@ -7,6 +7,9 @@
 namespace ebsd {
 
 static thread_local char g_error[512] = "";
+static unsigned long long g_launches = 0;
+
+void note_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -70,4 +73,5 @@ tensormap_encode_fn get_tensormap_encode() {
 extern "C" {
 int ebsd_abi_version(void) { return 1; }
 const char *ebsd_last_error(void) { return ebsd::g_error; }
+uint64_t ebsd_launch_count(void) { return __atomic_load_n(&ebsd::g_launches, __ATOMIC_RELAXED); }
 }

@@ -23,6 +23,14 @@ int sm_count();
         }                                                                                          \
     } while (0)
 
+// after every kernel launch: count it (ebsd_launch_count) and surface launch errors
+void note_launch();
+#define EBSD_LAUNCH_CHECK()                \
+    do {                                   \
+        ::ebsd::note_launch();             \
+        EBSD_CUDA_TRY(cudaGetLastError()); \
+    } while (0)
+
 #define EBSD_REQUIRE(cond, ...)                \
     do {                                       \
         if (!(cond)) {                         \

@@ -288,7 +288,7 @@ int ebsd_euler_to_quat(const double *euler_deg, int64_t n, double *quat, void *s
     const int threads = 256;
     euler_to_quat_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(euler_deg, n,
                                                                                                        quat);
-    EBSD_CUDA_TRY(cudaGetLastError());
+    EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }
 
@@ -325,7 +325,7 @@ int ebsd_consensus(const double *quat_table, int64_t N, const int64_t *cand_idx,
     p.ref_iter = ref_iter;
     const int wpb = 8;
     consensus_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(p);
-    EBSD_CUDA_TRY(cudaGetLastError());
+    EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }
 

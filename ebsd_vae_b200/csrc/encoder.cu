@@ -38,7 +38,7 @@ int launch_simt_conv(const float *in, const float *wt, float *raw, int hw, int n
     using C = SimtConvCfg<CIN, COUT>;
     dim3 grid((hw / 8) * (hw / 8), COUT / C::CO_TILE, nimg);
     conv3x3_simt_kernel<CIN, COUT><<<grid, C::THREADS, C::smem_floats * sizeof(float), st>>>(in, wt, raw, hw, hw);
-    EBSD_CUDA_TRY(cudaGetLastError());
+    EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }
 
@@ -61,7 +61,7 @@ int launch_stats(const float *raw, double *sums, int hw, int nimg, cudaStream_t 
     if (slices < 1) slices = 1;
     if (slices > 32) slices = 32;
     plane_stats_kernel<C><<<dim3(nimg, slices), 256, 0, st>>>(raw, sums, pixels);
-    EBSD_CUDA_TRY(cudaGetLastError());
+    EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }
 
@@ -72,7 +72,7 @@ int launch_finish(const float *raw, const double *sums, float *out, int hw, bool
     const unsigned blocks = (unsigned)((total + 255) / 256);
     if (pool) finish_f32_kernel<C, true><<<blocks, 256, 0, st>>>(raw, sums, out, hw, hw, nimg);
     else finish_f32_kernel<C, false><<<blocks, 256, 0, st>>>(raw, sums, out, hw, hw, nimg);
-    EBSD_CUDA_TRY(cudaGetLastError());
+    EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }
 
@@ -113,13 +113,13 @@ int ebsd_encoder_create(ebsd_encoder **out, const ebsd_weights *w, int device, v
         EBSD_CUDA_TRY(cudaMalloc(&enc->w_simt[i], (size_t)total * sizeof(float)));
         pack_conv_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w->conv_w[i], enc->w_simt[i], kPlan[i].cin,
                                                                     kPlan[i].cout);
-        EBSD_CUDA_TRY(cudaGetLastError());
+        EBSD_LAUNCH_CHECK();
     }
     EBSD_CUDA_TRY(cudaMalloc(&enc->wh, 32 * 2048 * sizeof(float)));
     EBSD_CUDA_TRY(cudaMalloc(&enc->bh, 32 * sizeof(float)));
     pack_head_weights_kernel<<<(32 * 2048 + 255) / 256, 256, 0, st>>>(w->mu_w, w->logvar_w, w->mu_b, w->logvar_b,
                                                                      enc->wh, enc->bh);
-    EBSD_CUDA_TRY(cudaGetLastError());
+    EBSD_LAUNCH_CHECK();
     EBSD_CUDA_TRY(cudaStreamSynchronize(st));  // the caller may free `w` right after create returns
     *out = enc;
     return EBSD_OK;
@@ -170,14 +170,14 @@ int ebsd_encoder_forward(ebsd_encoder *enc, const void *patterns, int dtype, int
             conv0_kernel<true><<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(pin, enc->w_simt[0], raw, nimg);
         else
             conv0_kernel<false><<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(pin, enc->w_simt[0], raw, nimg);
-        EBSD_CUDA_TRY(cudaGetLastError());
+        EBSD_LAUNCH_CHECK();
         if ((rc = stats_and_finish(0, raw, sums, act, nimg, st))) return rc;
         for (int l = 1; l < EBSD_N_CONV; ++l) {
             if ((rc = simt_conv_dispatch(l, act, enc->w_simt[l], raw, nimg, st))) return rc;
             if ((rc = stats_and_finish(l, raw, sums, act, nimg, st))) return rc;
         }
         heads_kernel<<<nimg, 256, 0, st>>>(act, enc->wh, enc->bh, mu + b0 * 16, logvar ? logvar + b0 * 16 : nullptr);
-        EBSD_CUDA_TRY(cudaGetLastError());
+        EBSD_LAUNCH_CHECK();
     }
     return EBSD_OK;
 }

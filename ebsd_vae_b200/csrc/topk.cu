@@ -411,7 +411,7 @@ static int launch_topk(const CUtensorMap &map, const TopkParams &p, int sms, cud
     const int n_items = p.n_qtiles * p.n_splits;
     const int grid = n_items < sms ? n_items : sms;
     topk_kernel<TQ><<<grid, kThreads, S::alloc, st>>>(map, p);
-    EBSD_CUDA_TRY(cudaGetLastError());
+    EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }
 
@@ -431,7 +431,7 @@ int ebsd_normalize_rows(float *x, int64_t n, int d, void *stream) {
     if (n == 0) return EBSD_OK;
     const int threads = 256;
     normalize_rows_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(x, n);
-    EBSD_CUDA_TRY(cudaGetLastError());
+    EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }
 
@@ -457,7 +457,7 @@ int ebsd_topk(const float *dict, int64_t N, int64_t index_base, const float *que
         const int wpb = 8;
         topk_merge_global_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, st>>>(
             nullptr, nullptr, 0, Q, k, out_dot, (long long *)out_idx, out_dist);
-        EBSD_CUDA_TRY(cudaGetLastError());
+        EBSD_LAUNCH_CHECK();
         return EBSD_OK;
     }
     EBSD_REQUIRE(dict != nullptr, "ebsd_topk: null dictionary");
@@ -508,7 +508,7 @@ int ebsd_topk(const float *dict, int64_t N, int64_t index_base, const float *que
         const int wpb = 8;
         topk_merge_parts_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, st>>>(
             p.parts, pl.n_splits, Q, k, index_base, out_dot, (long long *)out_idx, out_dist);
-        EBSD_CUDA_TRY(cudaGetLastError());
+        EBSD_LAUNCH_CHECK();
     }
     return EBSD_OK;
 }
@@ -524,7 +524,7 @@ int ebsd_topk_merge(const float *dots, const int64_t *idx, int R, int64_t Q, int
     const int wpb = 8;
     topk_merge_global_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
         dots, (const long long *)idx, R, Q, k, out_dot, (long long *)out_idx, out_dist);
-    EBSD_CUDA_TRY(cudaGetLastError());
+    EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }
 

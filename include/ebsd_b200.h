@@ -43,6 +43,8 @@ extern "C" {
 
 int ebsd_abi_version(void);
 const char *ebsd_last_error(void);
+/* Number of kernels this library has launched in this process (monotonic; for bench.py's gpu_launches). */
+uint64_t ebsd_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Encoder: VariationalAutoEncoderRawData.encoder + mu / logvar heads

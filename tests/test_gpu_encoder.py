@@ -63,9 +63,14 @@ def test_extreme_patterns(engine42):
     want, _ = R.encode(sd, R.u8_to_input(p))
     want = want.numpy()
     assert np.isfinite(mu).all()
-    err = np.linalg.norm(mu - want, axis=1) / np.maximum(np.linalg.norm(want, axis=1), 1e-3)
+    err = np.linalg.norm(mu - want, axis=1) / np.linalg.norm(want, axis=1)
     print("extreme rel", err)
-    assert err.max() < 5e-3  # constant planes are 0/0-like after InstanceNorm: looser bound, finite is the point
+    assert err[1:].max() < LATENT_REL_TOL
+    # An all-zero pattern gives exactly constant planes.  In exact arithmetic InstanceNorm maps them to zero and
+    # mu equals the head bias -- which is what the kernels produce (the conv bias is dropped analytically).
+    # torch's answer for this input is rounding noise of the plane mean amplified by rstd = 1/sqrt(eps) = 316
+    # per layer, so there is nothing to be in parity with.
+    np.testing.assert_allclose(mu[0], sd["mu.0.bias"].numpy(), atol=1e-6)
 
 
 def test_module_forward_returns_reference_tuple(engine42):
