@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "encoder_mma.cuh"
 #include "encoder_simt.cuh"
 
 namespace ebsd {
@@ -16,7 +17,8 @@ static const LayerPlan kPlan[EBSD_N_CONV] = {
     {128, 128, 32, true}, {128, 128, 16, false}, {128, 128, 16, true}, {128, 128, 8, false}, {128, 128, 8, true},
 };
 
-constexpr int kChunk = 32;                            // images per pass (keeps inter-layer traffic near L2)
+constexpr int kChunk = 32;                            // images per pass, SIMT path
+constexpr int kChunkMma = 256;                        // images per pass, tensor-core path (fills 148 SMs in late layers)
 constexpr size_t kRawFloats = 128ull * 128 * 32;      // largest raw / activation plane set per image
 constexpr size_t kSumsDoubles = 128 * 2;
 
@@ -24,7 +26,10 @@ constexpr size_t kSumsDoubles = 128 * 2;
 
 struct ebsd_encoder {
     int device;
+    int use_mma;                 // 1: tcgen05 path for conv 1..9, 0: fp32 SIMT path (EBSD_ENCODER_PATH=simt)
     float *w_simt[EBSD_N_CONV];  // [tap][ci][co] fp32
+    __half *w_mma[EBSD_N_CONV];  // tensor-path packing (encoder_mma.cuh), layers 1..9
+    CUtensorMap w_map[EBSD_N_CONV];
     float *wh;                   // [32][2048] permuted heads
     float *bh;                   // [32]
 };
@@ -92,6 +97,166 @@ int stats_and_finish(int layer, const float *raw, double *sums, float *out, int 
     }
 }
 
+
+int make_act_map(CUtensorMap *map, const __half *base, int cin, int hw, int nimg, int kc, int tw, int th, int tb) {
+    tensormap_encode_fn encode = get_tensormap_encode();
+    if (!encode) {
+        set_error("encoder: cuTensorMapEncodeTiled entry point not available");
+        return EBSD_ERR_CUDA;
+    }
+    const cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)hw, (cuuint64_t)hw, (cuuint64_t)nimg};
+    const cuuint64_t gstride[3] = {(cuuint64_t)cin * 2, (cuuint64_t)hw * cin * 2, (cuuint64_t)hw * hw * cin * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void *)base, gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               kc * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("encoder: cuTensorMapEncodeTiled(activations) failed with %d", (int)cr);
+        return EBSD_ERR_CUDA;
+    }
+    return EBSD_OK;
+}
+
+int make_weight_map(CUtensorMap *map, const __half *base, int cin, int cout, int kc) {
+    tensormap_encode_fn encode = get_tensormap_encode();
+    if (!encode) {
+        set_error("encoder: cuTensorMapEncodeTiled entry point not available");
+        return EBSD_ERR_CUDA;
+    }
+    const int rows = 9 * (cin / kc) * 2 * cout;
+    const cuuint64_t gdim[2] = {(cuuint64_t)kc, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)kc * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(2 * cout)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)base, gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               kc * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("encoder: cuTensorMapEncodeTiled(weights) failed with %d", (int)cr);
+        return EBSD_ERR_CUDA;
+    }
+    return EBSD_OK;
+}
+
+template <int CIN, int COUT, int W>
+int launch_mma_conv(const ebsd_encoder *enc, int layer, const __half *hi, const __half *lo, float *raw, double *sums,
+                    int nimg, cudaStream_t st) {
+    using C = MmaConvCfg<CIN, COUT, W>;
+    static bool configured = false;
+    if (!configured) {
+        EBSD_CUDA_TRY(cudaFuncSetAttribute(conv3x3_mma_kernel<CIN, COUT, W>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    CUtensorMap map_hi, map_lo;
+    int rc;
+    if ((rc = make_act_map(&map_hi, hi, CIN, W, nimg, C::KC, C::TW, C::TH, C::TB))) return rc;
+    if ((rc = make_act_map(&map_lo, lo, CIN, W, nimg, C::KC, C::TW, C::TH, C::TB))) return rc;
+    EBSD_CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)nimg * COUT * 2 * sizeof(double), st));
+    MmaConvParams p;
+    p.raw = raw;
+    p.sums = sums;
+    p.nimg = nimg;
+    p.ntiles = (W * W >= 128) ? nimg * ((W * W) / 128) : (nimg + C::TB - 1) / C::TB;
+    const int sms = sm_count();
+    const int grid = p.ntiles < sms ? p.ntiles : sms;
+    conv3x3_mma_kernel<CIN, COUT, W><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map_hi, map_lo, enc->w_map[layer], p);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}
+
+int mma_conv_dispatch(const ebsd_encoder *enc, int layer, const __half *hi, const __half *lo, float *raw, double *sums,
+                      int nimg, cudaStream_t st) {
+    switch (layer) {
+        case 1: return launch_mma_conv<32, 32, 128>(enc, layer, hi, lo, raw, sums, nimg, st);
+        case 2: return launch_mma_conv<32, 64, 64>(enc, layer, hi, lo, raw, sums, nimg, st);
+        case 3: return launch_mma_conv<64, 64, 64>(enc, layer, hi, lo, raw, sums, nimg, st);
+        case 4: return launch_mma_conv<64, 128, 32>(enc, layer, hi, lo, raw, sums, nimg, st);
+        case 5: return launch_mma_conv<128, 128, 32>(enc, layer, hi, lo, raw, sums, nimg, st);
+        case 6:
+        case 7: return launch_mma_conv<128, 128, 16>(enc, layer, hi, lo, raw, sums, nimg, st);
+        case 8:
+        case 9: return launch_mma_conv<128, 128, 8>(enc, layer, hi, lo, raw, sums, nimg, st);
+    }
+    set_error("encoder: no tensor-core kernel for layer %d", layer);
+    return EBSD_ERR_ARG;
+}
+
+template <int C>
+int launch_finish_split(const float *raw, const double *sums, __half *hi, __half *lo, int hw, bool pool, int nimg,
+                        cudaStream_t st) {
+    const int ho = pool ? hw / 2 : hw;
+    const long long total = (long long)nimg * ho * ho * (C / 4);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (pool) finish_split_kernel<C, true><<<blocks, 256, 0, st>>>(raw, sums, hi, lo, hw, hw, nimg);
+    else finish_split_kernel<C, false><<<blocks, 256, 0, st>>>(raw, sums, hi, lo, hw, hw, nimg);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}
+
+int finish_split_dispatch(int layer, const float *raw, const double *sums, __half *hi, __half *lo, int nimg,
+                          cudaStream_t st) {
+    const LayerPlan &L = kPlan[layer];
+    switch (L.cout) {
+        case 32: return launch_finish_split<32>(raw, sums, hi, lo, L.hw, L.pool, nimg, st);
+        case 64: return launch_finish_split<64>(raw, sums, hi, lo, L.hw, L.pool, nimg, st);
+        default: return launch_finish_split<128>(raw, sums, hi, lo, L.hw, L.pool, nimg, st);
+    }
+}
+
+int finish_f32_dispatch(int layer, const float *raw, const double *sums, float *out, int nimg, cudaStream_t st) {
+    const LayerPlan &L = kPlan[layer];
+    switch (L.cout) {
+        case 32: return launch_finish<32>(raw, sums, out, L.hw, L.pool, nimg, st);
+        case 64: return launch_finish<64>(raw, sums, out, L.hw, L.pool, nimg, st);
+        default: return launch_finish<128>(raw, sums, out, L.hw, L.pool, nimg, st);
+    }
+}
+
+template <int C>
+int stats_only(const float *raw, double *sums, int hw, int nimg, cudaStream_t st) {
+    return launch_stats<C>(raw, sums, hw, nimg, st);
+}
+
+// f32 NHWC -> fp16 hi / lo planes (debug hook only)
+__global__ void split_f32_kernel(const float *__restrict__ x, __half *__restrict__ hi, __half *__restrict__ lo,
+                                 long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+}
+
+// One chunk of the tensor-core path. Workspace: raw fp32 | hi fp16 | lo fp16 | sums.
+int forward_chunk_mma(const ebsd_encoder *enc, const void *pin, int dtype, int nimg, float *mu, float *logvar,
+                      float *raw, __half *hi, __half *lo, double *sums, cudaStream_t st) {
+    int rc;
+    const long long pairs = (long long)nimg * 128 * 64;
+    if (dtype == EBSD_PATTERN_U8)
+        conv0_kernel<true><<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(pin, enc->w_simt[0], raw, nimg);
+    else
+        conv0_kernel<false><<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(pin, enc->w_simt[0], raw, nimg);
+    EBSD_LAUNCH_CHECK();
+    if ((rc = stats_only<32>(raw, sums, 128, nimg, st))) return rc;
+    if ((rc = finish_split_dispatch(0, raw, sums, hi, lo, nimg, st))) return rc;
+    for (int l = 1; l < EBSD_N_CONV; ++l) {
+        if ((rc = mma_conv_dispatch(enc, l, hi, lo, raw, sums, nimg, st))) return rc;
+        if (l < EBSD_N_CONV - 1) {
+            if ((rc = finish_split_dispatch(l, raw, sums, hi, lo, nimg, st))) return rc;
+        } else {
+            if ((rc = finish_f32_dispatch(l, raw, sums, (float *)hi, nimg, st))) return rc;
+        }
+    }
+    heads_kernel<<<nimg, 256, 0, st>>>((const float *)hi, enc->wh, enc->bh, mu, logvar);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -115,6 +280,16 @@ int ebsd_encoder_create(ebsd_encoder **out, const ebsd_weights *w, int device, v
                                                                     kPlan[i].cout);
         EBSD_LAUNCH_CHECK();
     }
+    const char *path = getenv("EBSD_ENCODER_PATH");
+    enc->use_mma = !(path && strcmp(path, "simt") == 0);
+    for (int i = 1; i < EBSD_N_CONV; ++i) {
+        const int cin = kPlan[i].cin, cout = kPlan[i].cout, kc = cin < 64 ? cin : 64;
+        const int total = 9 * (cin / kc) * 2 * cout * kc;
+        EBSD_CUDA_TRY(cudaMalloc(&enc->w_mma[i], (size_t)total * sizeof(__half)));
+        pack_conv_weights_mma_kernel<<<(total + 255) / 256, 256, 0, st>>>(w->conv_w[i], enc->w_mma[i], cin, cout, kc);
+        EBSD_LAUNCH_CHECK();
+        if ((rc = make_weight_map(&enc->w_map[i], enc->w_mma[i], cin, cout, kc))) return rc;
+    }
     EBSD_CUDA_TRY(cudaMalloc(&enc->wh, 32 * 2048 * sizeof(float)));
     EBSD_CUDA_TRY(cudaMalloc(&enc->bh, 32 * sizeof(float)));
     pack_head_weights_kernel<<<(32 * 2048 + 255) / 256, 256, 0, st>>>(w->mu_w, w->logvar_w, w->mu_b, w->logvar_b,
@@ -128,15 +303,17 @@ int ebsd_encoder_create(ebsd_encoder **out, const ebsd_weights *w, int device, v
 void ebsd_encoder_destroy(ebsd_encoder *enc) {
     if (!enc) return;
     for (int i = 0; i < EBSD_N_CONV; ++i) cudaFree(enc->w_simt[i]);
+    for (int i = 1; i < EBSD_N_CONV; ++i) cudaFree(enc->w_mma[i]);
     cudaFree(enc->wh);
     cudaFree(enc->bh);
     free(enc);
 }
 
 size_t ebsd_encoder_workspace_bytes(const ebsd_encoder *enc, int64_t B) {
-    (void)enc;
     if (B <= 0) return 0;
-    const size_t nimg = (size_t)(B < kChunk ? B : kChunk);
+    const int chunk_cap = (enc && enc->use_mma) ? kChunkMma : kChunk;
+    const size_t nimg = (size_t)(B < chunk_cap ? B : chunk_cap);
+    // raw fp32 + (fp32 activations | fp16 hi + fp16 lo planes) + plane sums
     return nimg * (2 * kRawFloats * sizeof(float) + kSumsDoubles * sizeof(double)) + 256;
 }
 
@@ -155,13 +332,26 @@ int ebsd_encoder_forward(ebsd_encoder *enc, const void *patterns, int dtype, int
         return EBSD_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t chunk = (size_t)(B < kChunk ? B : kChunk);
+    const int chunk_cap = enc->use_mma ? kChunkMma : kChunk;
+    const size_t chunk = (size_t)(B < chunk_cap ? B : chunk_cap);
     uint8_t *ws = (uint8_t *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float *raw = (float *)ws;
     float *act = raw + chunk * kRawFloats;
     double *sums = (double *)(act + chunk * kRawFloats);
 
     const size_t px_bytes = dtype == EBSD_PATTERN_U8 ? 1 : 4;
+    if (enc->use_mma) {
+        __half *hi = (__half *)act;
+        __half *lo = hi + chunk * kRawFloats;
+        for (int64_t b0 = 0; b0 < B; b0 += kChunkMma) {
+            const int nimg = (int)((B - b0) < kChunkMma ? (B - b0) : kChunkMma);
+            const void *pin = (const uint8_t *)patterns + (size_t)b0 * 128 * 128 * px_bytes;
+            if ((rc = forward_chunk_mma(enc, pin, dtype, nimg, mu + b0 * 16, logvar ? logvar + b0 * 16 : nullptr, raw,
+                                        hi, lo, sums, st)))
+                return rc;
+        }
+        return EBSD_OK;
+    }
     for (int64_t b0 = 0; b0 < B; b0 += kChunk) {
         const int nimg = (int)((B - b0) < kChunk ? (B - b0) : kChunk);
         const void *pin = (const uint8_t *)patterns + (size_t)b0 * 128 * 128 * px_bytes;
@@ -180,6 +370,37 @@ int ebsd_encoder_forward(ebsd_encoder *enc, const void *patterns, int dtype, int
         EBSD_LAUNCH_CHECK();
     }
     return EBSD_OK;
+}
+
+
+int ebsd_debug_conv_layer(ebsd_encoder *enc, int layer, int use_mma, const float *act, int nimg, float *raw,
+                          double *sums, void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    EBSD_REQUIRE(enc && act && raw && sums, "ebsd_debug_conv_layer: null pointer");
+    EBSD_REQUIRE(layer >= 1 && layer < EBSD_N_CONV, "ebsd_debug_conv_layer: layer must be in [1,9]");
+    EBSD_REQUIRE(nimg >= 1, "ebsd_debug_conv_layer: nimg must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    const LayerPlan &L = kPlan[layer];
+    if (!use_mma) {
+        if ((rc = simt_conv_dispatch(layer, act, enc->w_simt[layer], raw, nimg, st))) return rc;
+        switch (L.cout) {
+            case 32: return launch_stats<32>(raw, sums, L.hw, nimg, st);
+            case 64: return launch_stats<64>(raw, sums, L.hw, nimg, st);
+            default: return launch_stats<128>(raw, sums, L.hw, nimg, st);
+        }
+    }
+    const long long n = (long long)nimg * L.hw * L.hw * L.cin;
+    const size_t need = (size_t)n * 2 * sizeof(__half) + 256;
+    if (!workspace || workspace_bytes < need) {
+        set_error("ebsd_debug_conv_layer: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return EBSD_ERR_WORKSPACE;
+    }
+    __half *hi = (__half *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    __half *lo = hi + n;
+    split_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(act, hi, lo, n);
+    EBSD_LAUNCH_CHECK();
+    return mma_conv_dispatch(enc, layer, hi, lo, raw, sums, nimg, st);
 }
 
 }  // extern "C"

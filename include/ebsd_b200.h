@@ -74,6 +74,12 @@ size_t ebsd_encoder_workspace_bytes(const ebsd_encoder *enc, int64_t B);
 int ebsd_encoder_forward(ebsd_encoder *enc, const void *patterns, int dtype, int64_t B, float *mu, float *logvar,
                          void *workspace, size_t workspace_bytes, void *stream);
 
+/* Test hook: run convolution `layer` (1..9) alone on finished activations act [nimg,H,W,Cin] fp32 NHWC and return the
+ * raw (pre-InstanceNorm) output raw [nimg,H,W,Cout] fp32 NHWC plus the plane sums [nimg,Cout,2] (sum, sum of squares).
+ * use_mma = 1: tcgen05 path (workspace >= nimg*H*W*Cin*4 + 256 bytes), 0: fp32 CUDA-core path. */
+int ebsd_debug_conv_layer(ebsd_encoder *enc, int layer, int use_mma, const float *act, int nimg, float *raw,
+                          double *sums, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Latent dictionary: exact cosine top-k
  *   replaces FaissLatentVectorDatabase._l2_normalize / add_vectors / query_similar

@@ -1,0 +1,61 @@
+"""GPU parity, layer by layer: the tcgen05 implicit-GEMM convolution (and the fp32 CUDA-core one) against
+torch's fp32 conv2d on the same activations.  Localises a failure to one layer / one tile shape."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import encoder_ref as R
+
+pytestmark = pytest.mark.gpu
+
+PLAN = {1: (32, 32, 128), 2: (32, 64, 64), 3: (64, 64, 64), 4: (64, 128, 32), 5: (128, 128, 32), 6: (128, 128, 16),
+        7: (128, 128, 16), 8: (128, 128, 8), 9: (128, 128, 8)}
+IDX = {1: 1, 2: 3, 3: 4, 4: 6, 5: 7, 6: 9, 7: 10, 8: 12, 9: 13}
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import ebsd_vae_b200 as E
+    sd = R.make_state_dict(42)
+    return E.EncoderEngine(sd, "cuda"), sd
+
+
+def _run_layer(eng, layer, act_nhwc, use_mma):
+    from ebsd_vae_b200 import _native
+    lib = _native.load()
+    cin, cout, hw = PLAN[layer]
+    n = act_nhwc.shape[0]
+    raw = torch.full((n, hw, hw, cout), float("nan"), dtype=torch.float32, device="cuda")
+    sums = torch.zeros((n, cout, 2), dtype=torch.float64, device="cuda")
+    ws = torch.empty(act_nhwc.numel() * 4 + 512, dtype=torch.uint8, device="cuda")
+    _native.check(lib.ebsd_debug_conv_layer(eng._handle, layer, int(use_mma), act_nhwc.data_ptr(), n, raw.data_ptr(),
+                                            sums.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            torch.cuda.current_stream().cuda_stream), "ebsd_debug_conv_layer")
+    torch.cuda.synchronize()
+    return raw, sums
+
+
+@pytest.mark.parametrize("use_mma", [0, 1])
+@pytest.mark.parametrize("layer,nimg", [(1, 1), (1, 3), (2, 2), (3, 3), (4, 5), (5, 4), (6, 7), (7, 16), (8, 1), (8, 5),
+                                        (9, 2), (9, 37)])
+def test_conv_layer_matches_torch(engine, layer, nimg, use_mma):
+    eng, sd = engine
+    cin, cout, hw = PLAN[layer]
+    g = torch.Generator().manual_seed(1000 * layer + nimg)
+    x = torch.randn((nimg, cin, hw, hw), generator=g)
+    x = torch.where(x > 0, x, 0.02 * x)  # looks like a LeakyReLU output
+    w = sd[f"encoder.{IDX[layer]}.0.weight"]
+    want = F.conv2d(x.double(), w.double(), None, padding=1).permute(0, 2, 3, 1).contiguous()  # NHWC, fp64 truth
+    act = x.permute(0, 2, 3, 1).contiguous().cuda()
+    raw, sums = _run_layer(eng, layer, act, use_mma)
+    got = raw.cpu().double()
+    assert torch.isfinite(got).all(), "kernel left part of the output unwritten"
+    scale = want.abs().max().item()
+    err = (got - want).abs().max().item() / scale
+    print(f"layer {layer} nimg {nimg} mma={use_mma}: max err / max |y| = {err:.3e}")
+    assert err < 2e-5
+    s1 = want.sum(dim=(1, 2))
+    s2 = (want * want).sum(dim=(1, 2))
+    np.testing.assert_allclose(sums[:, :, 0].cpu().numpy(), s1.numpy(), rtol=0, atol=2e-5 * scale * hw * hw)
+    np.testing.assert_allclose(sums[:, :, 1].cpu().numpy(), s2.numpy(), rtol=1e-4)
