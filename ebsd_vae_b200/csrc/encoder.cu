@@ -3,7 +3,9 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "encoder_finish.cuh"
 #include "encoder_mma.cuh"
+#include "encoder_mma2.cuh"
 #include "encoder_simt.cuh"
 
 namespace ebsd {
@@ -26,7 +28,8 @@ constexpr size_t kSumsDoubles = 128 * 2;
 
 struct ebsd_encoder {
     int device;
-    int use_mma;                 // 1: tcgen05 path for conv 1..9, 0: fp32 SIMT path (EBSD_ENCODER_PATH=simt)
+    int use_mma;                 // EBSD_ENCODER_PATH: 2 = tcgen05 shifted-window path (default, "mma"), 1 = first-generation
+                                 // tcgen05 path ("mma1"), 0 = fp32 CUDA-core path ("simt")
     float *w_simt[EBSD_N_CONV];  // [tap][ci][co] fp32
     __half *w_mma[EBSD_N_CONV];  // tensor-path packing (encoder_mma.cuh), layers 1..9
     CUtensorMap w_map[EBSD_N_CONV];
@@ -58,6 +61,19 @@ int simt_conv_dispatch(int layer, const float *in, const float *wt, float *raw, 
     return EBSD_ERR_ARG;
 }
 
+template <int C, int MODE>
+int launch_finish_generic(const float *raw, const double *sums, void *out_a, void *out_b, int hw, bool pool, int nimg,
+                          cudaStream_t st) {
+    const int ho = pool ? hw / 2 : hw;
+    const int hq = ho + (MODE == FIN_SPLIT_PAD ? 2 : 0);
+    const int items = hq * hq * (C / 4);
+    const dim3 grid((items + 256 * kFinishItemsPerThread - 1) / (256 * kFinishItemsPerThread), nimg);
+    if (pool) finish_kernel<C, true, MODE><<<grid, 256, 0, st>>>(raw, sums, out_a, out_b, hw, hw);
+    else finish_kernel<C, false, MODE><<<grid, 256, 0, st>>>(raw, sums, out_a, out_b, hw, hw);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}
+
 template <int C>
 int launch_stats(const float *raw, double *sums, int hw, int nimg, cudaStream_t st) {
     EBSD_CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)nimg * C * 2 * sizeof(double), st));
@@ -72,13 +88,7 @@ int launch_stats(const float *raw, double *sums, int hw, int nimg, cudaStream_t 
 
 template <int C>
 int launch_finish(const float *raw, const double *sums, float *out, int hw, bool pool, int nimg, cudaStream_t st) {
-    const int ho = pool ? hw / 2 : hw;
-    const long long total = (long long)nimg * ho * ho * (C / 4);
-    const unsigned blocks = (unsigned)((total + 255) / 256);
-    if (pool) finish_f32_kernel<C, true><<<blocks, 256, 0, st>>>(raw, sums, out, hw, hw, nimg);
-    else finish_f32_kernel<C, false><<<blocks, 256, 0, st>>>(raw, sums, out, hw, hw, nimg);
-    EBSD_LAUNCH_CHECK();
-    return EBSD_OK;
+    return launch_finish_generic<C, FIN_F32>(raw, sums, out, nullptr, hw, pool, nimg, st);
 }
 
 int stats_and_finish(int layer, const float *raw, double *sums, float *out, int nimg, cudaStream_t st) {
@@ -188,13 +198,7 @@ int mma_conv_dispatch(const ebsd_encoder *enc, int layer, const __half *hi, cons
 template <int C>
 int launch_finish_split(const float *raw, const double *sums, __half *hi, __half *lo, int hw, bool pool, int nimg,
                         cudaStream_t st) {
-    const int ho = pool ? hw / 2 : hw;
-    const long long total = (long long)nimg * ho * ho * (C / 4);
-    const unsigned blocks = (unsigned)((total + 255) / 256);
-    if (pool) finish_split_kernel<C, true><<<blocks, 256, 0, st>>>(raw, sums, hi, lo, hw, hw, nimg);
-    else finish_split_kernel<C, false><<<blocks, 256, 0, st>>>(raw, sums, hi, lo, hw, hw, nimg);
-    EBSD_LAUNCH_CHECK();
-    return EBSD_OK;
+    return launch_finish_generic<C, FIN_SPLIT>(raw, sums, hi, lo, hw, pool, nimg, st);
 }
 
 int finish_split_dispatch(int layer, const float *raw, const double *sums, __half *hi, __half *lo, int nimg,
@@ -230,6 +234,172 @@ __global__ void split_f32_kernel(const float *__restrict__ x, __half *__restrict
     const __half h = __float2half_rn(v);
     hi[i] = h;
     lo[i] = __float2half_rn(v - __half2float(h));
+}
+
+int g_debug_flags = 0;  // ebsd_debug_set_flags (profiling switches of conv3x3_mma2_kernel)
+
+// ------------------------------------------------------------------ second-generation tensor path (encoder_mma2.cuh)
+int make_plane_map(CUtensorMap *map, const __half *base, int cin, long long rows, int kc, int box_rows) {
+    tensormap_encode_fn encode = get_tensormap_encode();
+    if (!encode) {
+        set_error("encoder: cuTensorMapEncodeTiled entry point not available");
+        return EBSD_ERR_CUDA;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)cin, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)cin * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)base, gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               kc * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("encoder: cuTensorMapEncodeTiled(padded plane) failed with %d", (int)cr);
+        return EBSD_ERR_CUDA;
+    }
+    return EBSD_OK;
+}
+
+template <int CIN, int COUT, int W>
+int launch_mma2_conv(const ebsd_encoder *enc, int layer, const __half *hi, const __half *lo, float *raw, double *sums,
+                     int nimg, cudaStream_t st) {
+    using C = Mma2Cfg<CIN, COUT, W>;
+    static bool configured = false;
+    if (!configured) {
+        EBSD_CUDA_TRY(cudaFuncSetAttribute(conv3x3_mma2_kernel<CIN, COUT, W>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    const long long rows = (long long)nimg * C::HP * C::WP;
+    CUtensorMap map_hi, map_lo;
+    int rc;
+    if ((rc = make_plane_map(&map_hi, hi, CIN, rows, C::KC, C::BOXR))) return rc;
+    if ((rc = make_plane_map(&map_lo, lo, CIN, rows, C::KC, C::BOXR))) return rc;
+    EBSD_CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)nimg * COUT * 2 * sizeof(double), st));
+    Mma2Params p;
+    p.raw = raw;
+    p.sums = sums;
+    p.nimg = nimg;
+    p.ntiles = (int)((rows + 127) / 128);
+    p.dbg = g_debug_flags;
+    const int sms = sm_count();
+    const int grid = p.ntiles < sms ? p.ntiles : sms;
+    conv3x3_mma2_kernel<CIN, COUT, W><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map_hi, map_lo, enc->w_map[layer], p);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}
+
+// layers 1..5 (W >= 32) have a second-generation kernel
+int mma2_conv_dispatch(const ebsd_encoder *enc, int layer, const __half *hi, const __half *lo, float *raw,
+                       double *sums, int nimg, cudaStream_t st) {
+    switch (layer) {
+        case 1: return launch_mma2_conv<32, 32, 128>(enc, layer, hi, lo, raw, sums, nimg, st);
+        case 2: return launch_mma2_conv<32, 64, 64>(enc, layer, hi, lo, raw, sums, nimg, st);
+        case 3: return launch_mma2_conv<64, 64, 64>(enc, layer, hi, lo, raw, sums, nimg, st);
+        case 4: return launch_mma2_conv<64, 128, 32>(enc, layer, hi, lo, raw, sums, nimg, st);
+        case 5: return launch_mma2_conv<128, 128, 32>(enc, layer, hi, lo, raw, sums, nimg, st);
+    }
+    set_error("encoder: no second-generation kernel for layer %d", layer);
+    return EBSD_ERR_ARG;
+}
+
+template <int C>
+int launch_finish_split_padded(const float *raw, const double *sums, __half *hi, __half *lo, int hw, bool pool,
+                               int nimg, cudaStream_t st) {
+    return launch_finish_generic<C, FIN_SPLIT_PAD>(raw, sums, hi, lo, hw, pool, nimg, st);
+}
+
+int finish_split_padded_dispatch(int layer, const float *raw, const double *sums, __half *hi, __half *lo, int nimg,
+                                 cudaStream_t st) {
+    const LayerPlan &L = kPlan[layer];
+    switch (L.cout) {
+        case 32: return launch_finish_split_padded<32>(raw, sums, hi, lo, L.hw, L.pool, nimg, st);
+        case 64: return launch_finish_split_padded<64>(raw, sums, hi, lo, L.hw, L.pool, nimg, st);
+        default: return launch_finish_split_padded<128>(raw, sums, hi, lo, L.hw, L.pool, nimg, st);
+    }
+}
+
+// Workspace of the second-generation path for a chunk of `chunk` images, early layers in sub-chunks of `sub`:
+//   raw | early planes (hi, lo) | late planes (hi, lo) | sums
+struct Mma2Workspace {
+    float *raw;
+    __half *early_hi, *early_lo;   // inputs of conv 1..3 for one sub-chunk
+    __half *late_hi, *late_lo;     // inputs of conv 4..9 (and the final fp32 features) for the whole chunk
+    double *sums;
+    size_t bytes;
+};
+constexpr int kSub = 24;                                     // images per early sub-chunk (keeps ~100 MB in L2)
+constexpr size_t kEarlyPlaneHalfs = 130ull * 130 * 32;       // largest early plane per image (conv1 input)
+constexpr size_t kLatePlaneHalfs = 34ull * 34 * 128;         // largest late plane per image (conv5 input)
+constexpr size_t kLateRawFloats = 32ull * 32 * 128;          // largest raw output of conv 4..9 per image
+
+Mma2Workspace carve_mma2(void *workspace, size_t chunk) {
+    const size_t sub = chunk < (size_t)kSub ? chunk : (size_t)kSub;
+    uint8_t *p = (uint8_t *)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    auto take = [&](size_t bytes) {
+        uint8_t *r = p;
+        p += (bytes + 1023) & ~(size_t)1023;
+        return r;
+    };
+    Mma2Workspace w;
+    const size_t raw_floats = sub * kRawFloats > chunk * kLateRawFloats ? sub * kRawFloats : chunk * kLateRawFloats;
+    w.raw = (float *)take(raw_floats * sizeof(float));
+    w.early_hi = (__half *)take(sub * kEarlyPlaneHalfs * sizeof(__half));
+    w.early_lo = (__half *)take(sub * kEarlyPlaneHalfs * sizeof(__half));
+    w.late_hi = (__half *)take(chunk * kLatePlaneHalfs * sizeof(__half));
+    w.late_lo = (__half *)take(chunk * kLatePlaneHalfs * sizeof(__half));
+    w.sums = (double *)take(chunk * kSumsDoubles * sizeof(double));
+    w.bytes = (size_t)(p - (uint8_t *)workspace);
+    return w;
+}
+
+// One chunk (<= kChunkMma images) of the second-generation path.
+int forward_chunk_mma2(const ebsd_encoder *enc, const void *pin, int dtype, int nimg, float *mu, float *logvar,
+                       const Mma2Workspace &w, cudaStream_t st) {
+    int rc;
+    const size_t px_bytes = dtype == EBSD_PATTERN_U8 ? 1 : 4;
+    // ---- layers 0..3 in L2-sized sub-chunks; conv3's finisher deposits into the chunk-level planes
+    for (int s0 = 0; s0 < nimg; s0 += kSub) {
+        const int ns = nimg - s0 < kSub ? nimg - s0 : kSub;
+        const void *pats = (const uint8_t *)pin + (size_t)s0 * 128 * 128 * px_bytes;
+        EBSD_CUDA_TRY(cudaMemsetAsync(w.sums, 0, (size_t)ns * 32 * 2 * sizeof(double), st));
+        if (dtype == EBSD_PATTERN_U8) conv0_stats_kernel<true><<<dim3(16, ns), 256, 0, st>>>(pats, enc->w_simt[0], w.sums);
+        else conv0_stats_kernel<false><<<dim3(16, ns), 256, 0, st>>>(pats, enc->w_simt[0], w.sums);
+        EBSD_LAUNCH_CHECK();
+        if (dtype == EBSD_PATTERN_U8)
+            conv0_finish_kernel<true><<<dim3(16, ns), 256, 0, st>>>(pats, enc->w_simt[0], w.sums, w.early_hi, w.early_lo);
+        else
+            conv0_finish_kernel<false><<<dim3(16, ns), 256, 0, st>>>(pats, enc->w_simt[0], w.sums, w.early_hi, w.early_lo);
+        EBSD_LAUNCH_CHECK();
+        for (int l = 1; l <= 3; ++l) {
+            if ((rc = mma2_conv_dispatch(enc, l, w.early_hi, w.early_lo, w.raw, w.sums, ns, st))) return rc;
+            if (l < 3) {
+                if ((rc = finish_split_padded_dispatch(l, w.raw, w.sums, w.early_hi, w.early_lo, ns, st))) return rc;
+            } else {  // conv3 -> pooled 32x32x64, padded 34x34: chunk-level buffer at image offset s0
+                const size_t off = (size_t)s0 * 34 * 34 * 64;
+                if ((rc = finish_split_padded_dispatch(l, w.raw, w.sums, w.late_hi + off, w.late_lo + off, ns, st)))
+                    return rc;
+            }
+        }
+    }
+    // ---- layers 4..9 over the whole chunk
+    for (int l = 4; l < EBSD_N_CONV; ++l) {
+        if (l <= 5) {
+            if ((rc = mma2_conv_dispatch(enc, l, w.late_hi, w.late_lo, w.raw, w.sums, nimg, st))) return rc;
+        } else {
+            if ((rc = mma_conv_dispatch(enc, l, w.late_hi, w.late_lo, w.raw, w.sums, nimg, st))) return rc;
+        }
+        if (l == 4) {  // next layer (5) reads padded planes
+            if ((rc = finish_split_padded_dispatch(l, w.raw, w.sums, w.late_hi, w.late_lo, nimg, st))) return rc;
+        } else if (l < EBSD_N_CONV - 1) {  // layers 6..9 read un-padded planes (first-generation kernel)
+            if ((rc = finish_split_dispatch(l, w.raw, w.sums, w.late_hi, w.late_lo, nimg, st))) return rc;
+        } else {
+            if ((rc = finish_f32_dispatch(l, w.raw, w.sums, (float *)w.late_hi, nimg, st))) return rc;
+        }
+    }
+    heads_kernel<<<nimg, 256, 0, st>>>((const float *)w.late_hi, enc->wh, enc->bh, mu, logvar);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
 }
 
 // One chunk of the tensor-core path. Workspace: raw fp32 | hi fp16 | lo fp16 | sums.
@@ -281,7 +451,9 @@ int ebsd_encoder_create(ebsd_encoder **out, const ebsd_weights *w, int device, v
         EBSD_LAUNCH_CHECK();
     }
     const char *path = getenv("EBSD_ENCODER_PATH");
-    enc->use_mma = !(path && strcmp(path, "simt") == 0);
+    enc->use_mma = 2;
+    if (path && strcmp(path, "simt") == 0) enc->use_mma = 0;
+    if (path && strcmp(path, "mma1") == 0) enc->use_mma = 1;
     for (int i = 1; i < EBSD_N_CONV; ++i) {
         const int cin = kPlan[i].cin, cout = kPlan[i].cout, kc = cin < 64 ? cin : 64;
         const int total = 9 * (cin / kc) * 2 * cout * kc;
@@ -313,6 +485,7 @@ size_t ebsd_encoder_workspace_bytes(const ebsd_encoder *enc, int64_t B) {
     if (B <= 0) return 0;
     const int chunk_cap = (enc && enc->use_mma) ? kChunkMma : kChunk;
     const size_t nimg = (size_t)(B < chunk_cap ? B : chunk_cap);
+    if (enc && enc->use_mma == 2) return carve_mma2(nullptr, nimg).bytes + 1024;
     // raw fp32 + (fp32 activations | fp16 hi + fp16 lo planes) + plane sums
     return nimg * (2 * kRawFloats * sizeof(float) + kSumsDoubles * sizeof(double)) + 256;
 }
@@ -340,6 +513,17 @@ int ebsd_encoder_forward(ebsd_encoder *enc, const void *patterns, int dtype, int
     double *sums = (double *)(act + chunk * kRawFloats);
 
     const size_t px_bytes = dtype == EBSD_PATTERN_U8 ? 1 : 4;
+    if (enc->use_mma == 2) {
+        const Mma2Workspace w2 = carve_mma2(workspace, chunk);
+        for (int64_t b0 = 0; b0 < B; b0 += kChunkMma) {
+            const int nimg = (int)((B - b0) < kChunkMma ? (B - b0) : kChunkMma);
+            const void *pin = (const uint8_t *)patterns + (size_t)b0 * 128 * 128 * px_bytes;
+            if ((rc = forward_chunk_mma2(enc, pin, dtype, nimg, mu + b0 * 16, logvar ? logvar + b0 * 16 : nullptr, w2,
+                                         st)))
+                return rc;
+        }
+        return EBSD_OK;
+    }
     if (enc->use_mma) {
         __half *hi = (__half *)act;
         __half *lo = hi + chunk * kRawFloats;
@@ -390,6 +574,20 @@ int ebsd_debug_conv_layer(ebsd_encoder *enc, int layer, int use_mma, const float
             default: return launch_stats<128>(raw, sums, L.hw, nimg, st);
         }
     }
+    if (use_mma == 2) {
+        EBSD_REQUIRE(layer <= 5, "ebsd_debug_conv_layer: the shifted-window kernel covers layers 1..5");
+        const long long np = (long long)nimg * (L.hw + 2) * (L.hw + 2) * L.cin;
+        const size_t need2 = (size_t)np * 2 * sizeof(__half) + 2048;
+        if (!workspace || workspace_bytes < need2) {
+            set_error("ebsd_debug_conv_layer: workspace too small (%zu < %zu)", workspace_bytes, need2);
+            return EBSD_ERR_WORKSPACE;
+        }
+        __half *phi = (__half *)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+        __half *plo = phi + ((np + 511) / 512) * 512;
+        split_pad_f32_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(act, phi, plo, L.hw, L.hw, L.cin, nimg);
+        EBSD_LAUNCH_CHECK();
+        return mma2_conv_dispatch(enc, layer, phi, plo, raw, sums, nimg, st);
+    }
     const long long n = (long long)nimg * L.hw * L.hw * L.cin;
     const size_t need = (size_t)n * 2 * sizeof(__half) + 256;
     if (!workspace || workspace_bytes < need) {
@@ -402,5 +600,7 @@ int ebsd_debug_conv_layer(ebsd_encoder *enc, int layer, int use_mma, const float
     EBSD_LAUNCH_CHECK();
     return mma_conv_dispatch(enc, layer, hi, lo, raw, sums, nimg, st);
 }
+
+void ebsd_debug_set_flags(int flags) { g_debug_flags = flags; }
 
 }  // extern "C"

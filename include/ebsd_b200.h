@@ -80,6 +80,9 @@ int ebsd_encoder_forward(ebsd_encoder *enc, const void *patterns, int dtype, int
 int ebsd_debug_conv_layer(ebsd_encoder *enc, int layer, int use_mma, const float *act, int nimg, float *raw,
                           double *sums, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Profiling hook: switches parts of the shifted-window conv kernel off (results are then wrong). 0 = normal. */
+void ebsd_debug_set_flags(int flags);
+
 /* ---------------------------------------------------------------------------------------------
  * Latent dictionary: exact cosine top-k
  *   replaces FaissLatentVectorDatabase._l2_normalize / add_vectors / query_similar

@@ -61,7 +61,7 @@ def test_encode_apis_match_oracle(setup):
     assert many.shape == (10, 16)
     rel = np.linalg.norm(many - mu[:10], axis=1) / np.linalg.norm(mu[:10], axis=1)
     assert rel.max() < 1e-3
-    np.testing.assert_allclose(one, many[3], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(one, many[3], rtol=0, atol=1e-5)  # plane sums are accumulated in tile order
     t = indexer.encode_pattern(torch.from_numpy(u8[3].astype(np.float32) / 255.0))  # tensors bypass the transform
     np.testing.assert_allclose(t, one, rtol=0, atol=1e-5)
 
