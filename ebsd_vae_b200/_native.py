@@ -49,6 +49,8 @@ SYMBOLS = {
     "ebsd_debug_conv_layer": (_int, [_c_void_p, _int, _int, _c_void_p, _int, _c_void_p, _c_void_p, _c_void_p, _size_t,
                                      _c_void_p]),
     "ebsd_debug_set_flags": (None, [_int]),
+    "ebsd_debug_fused_layer": (_int, [_c_void_p, _int, _int, _c_void_p, _c_void_p, _int, _int, _c_void_p, _c_void_p,
+                                      _c_void_p]),
     "ebsd_normalize_rows": (_int, [_c_void_p, _i64, _int, _c_void_p]),
     "ebsd_topk_workspace_bytes": (_size_t, [_i64, _i64, _int]),
     "ebsd_topk": (_int, [_c_void_p, _i64, _i64, _c_void_p, _i64, _int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,

@@ -6,6 +6,7 @@
 #include "encoder_finish.cuh"
 #include "encoder_mma.cuh"
 #include "encoder_mma2.cuh"
+#include "encoder_fused.cuh"
 #include "encoder_simt.cuh"
 
 namespace ebsd {
@@ -28,8 +29,10 @@ constexpr size_t kSumsDoubles = 128 * 2;
 
 struct ebsd_encoder {
     int device;
-    int use_mma;                 // EBSD_ENCODER_PATH: 2 = tcgen05 shifted-window path (default, "mma"), 1 = first-generation
+    int use_mma;                 // EBSD_ENCODER_PATH: 3 = fused producer/tcgen05/epilogue blocks (default, "fused"),
+                                 // 2 = tcgen05 shifted-window path with finisher kernels ("mma"), 1 = first-generation
                                  // tcgen05 path ("mma1"), 0 = fp32 CUDA-core path ("simt")
+    int chunk;                   // images per pass of the fused path (EBSD_ENCODER_CHUNK)
     float *w_simt[EBSD_N_CONV];  // [tap][ci][co] fp32
     __half *w_mma[EBSD_N_CONV];  // tensor-path packing (encoder_mma.cuh), layers 1..9
     CUtensorMap w_map[EBSD_N_CONV];
@@ -402,6 +405,112 @@ int forward_chunk_mma2(const ebsd_encoder *enc, const void *pin, int dtype, int 
     return EBSD_OK;
 }
 
+
+// ------------------------------------------------------------------ third-generation path (encoder_fused.cuh)
+constexpr int kChunkFused = 296;                       // default images per pass (2 per SM: every late layer fills the GPU)
+constexpr size_t kFusedBuf0Floats = 64ull * 64 * 32;   // per image: pooled output of conv1 (largest tenant of buffer 0)
+constexpr size_t kFusedBuf1Floats = 64ull * 64 * 64;   // per image: output of conv2 (largest tenant of buffer 1)
+
+struct FusedWorkspace {
+    float *buf0, *buf1;
+    double *sums;  // [EBSD_N_CONV][chunk][128][2]
+    size_t bytes;
+};
+
+FusedWorkspace carve_fused(void *workspace, size_t chunk) {
+    uint8_t *p = (uint8_t *)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    auto take = [&](size_t bytes) {
+        uint8_t *r = p;
+        p += (bytes + 1023) & ~(size_t)1023;
+        return r;
+    };
+    FusedWorkspace w;
+    w.buf0 = (float *)take(chunk * kFusedBuf0Floats * sizeof(float));
+    w.buf1 = (float *)take(chunk * kFusedBuf1Floats * sizeof(float));
+    w.sums = (double *)take((size_t)EBSD_N_CONV * chunk * kSumsDoubles * sizeof(double));
+    w.bytes = (size_t)(p - (uint8_t *)workspace);
+    return w;
+}
+
+template <int CIN, int COUT, int W, int SRC>
+int launch_fused(const ebsd_encoder *enc, int layer, const void *src, const double *src_sums, int src_plane,
+                 float *raw, double *sums, int nimg, bool pool, cudaStream_t st) {
+    using C = FusedCfg<CIN, COUT, W, SRC>;
+    static bool configured = false;
+    if (!configured) {
+        EBSD_CUDA_TRY(cudaFuncSetAttribute(conv3x3_fused_kernel<CIN, COUT, W, SRC>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    FusedParams p;
+    p.src = src;
+    p.src_sums = src_sums;
+    p.inv_src_plane = 1.0 / (double)src_plane;
+    p.w0 = enc->w_simt[0];
+    p.raw = raw;
+    p.sums = sums;
+    p.nimg = nimg;
+    p.nitems = C::NI == 1 ? nimg * C::ITEMS_PER_IMAGE : (nimg + C::NI - 1) / C::NI;
+    p.pool = pool ? 1 : 0;
+    const int sms = sm_count();
+    const int per = (p.nitems + sms - 1) / sms;
+    const int grid = (p.nitems + per - 1) / per;
+    conv3x3_fused_kernel<CIN, COUT, W, SRC><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(enc->w_map[layer], p);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}
+
+// src: layer 1 -> patterns (dtype), layers 2..9 -> raw output of layer-1 ... ; sums must be zeroed by the caller
+int fused_dispatch(const ebsd_encoder *enc, int layer, int dtype, const void *src, const double *src_sums,
+                   int src_plane, float *raw, double *sums, int nimg, cudaStream_t st) {
+    const bool pool = kPlan[layer].pool;
+    switch (layer) {
+        case 1:
+            if (dtype == EBSD_PATTERN_U8)
+                return launch_fused<32, 32, 128, SRC_U8>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
+            return launch_fused<32, 32, 128, SRC_F32>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
+        case 2: return launch_fused<32, 64, 64, SRC_RAW>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
+        case 3: return launch_fused<64, 64, 64, SRC_RAW>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
+        case 4: return launch_fused<64, 128, 32, SRC_RAW>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
+        case 5: return launch_fused<128, 128, 32, SRC_RAW>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
+        case 6:
+        case 7: return launch_fused<128, 128, 16, SRC_RAW>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
+        case 8:
+        case 9: return launch_fused<128, 128, 8, SRC_RAW>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
+    }
+    set_error("encoder: no fused kernel for layer %d", layer);
+    return EBSD_ERR_ARG;
+}
+
+int conv0_stats(const ebsd_encoder *enc, const void *pats, int dtype, int nimg, double *sums0, cudaStream_t st) {
+    if (dtype == EBSD_PATTERN_U8) conv0_stats_kernel<true><<<dim3(16, nimg), 256, 0, st>>>(pats, enc->w_simt[0], sums0);
+    else conv0_stats_kernel<false><<<dim3(16, nimg), 256, 0, st>>>(pats, enc->w_simt[0], sums0);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}
+
+// One chunk of the fused path: 12 launches (statistics of conv0, nine fused blocks, heads) + one memset.
+int forward_chunk_fused(const ebsd_encoder *enc, const void *pin, int dtype, int nimg, size_t chunk, float *mu,
+                        float *logvar, const FusedWorkspace &w, cudaStream_t st) {
+    int rc;
+    const size_t lstride = chunk * kSumsDoubles;  // doubles per layer in w.sums
+    EBSD_CUDA_TRY(cudaMemsetAsync(w.sums, 0, (size_t)EBSD_N_CONV * lstride * sizeof(double), st));
+    if ((rc = conv0_stats(enc, pin, dtype, nimg, w.sums, st))) return rc;
+    const void *src = pin;
+    for (int l = 1; l < EBSD_N_CONV; ++l) {
+        float *dst = (l & 1) ? w.buf0 : w.buf1;
+        const int src_plane = kPlan[l - 1].hw * kPlan[l - 1].hw;
+        if ((rc = fused_dispatch(enc, l, dtype, src, w.sums + (size_t)(l - 1) * lstride, src_plane, dst,
+                                 w.sums + (size_t)l * lstride, nimg, st)))
+            return rc;
+        src = dst;
+    }
+    heads_norm_kernel<<<nimg, 256, 0, st>>>((const float *)src, w.sums + (size_t)(EBSD_N_CONV - 1) * lstride, enc->wh,
+                                           enc->bh, mu, logvar);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}
+
 // One chunk of the tensor-core path. Workspace: raw fp32 | hi fp16 | lo fp16 | sums.
 int forward_chunk_mma(const ebsd_encoder *enc, const void *pin, int dtype, int nimg, float *mu, float *logvar,
                       float *raw, __half *hi, __half *lo, double *sums, cudaStream_t st) {
@@ -451,9 +560,15 @@ int ebsd_encoder_create(ebsd_encoder **out, const ebsd_weights *w, int device, v
         EBSD_LAUNCH_CHECK();
     }
     const char *path = getenv("EBSD_ENCODER_PATH");
-    enc->use_mma = 2;
+    enc->use_mma = 3;
     if (path && strcmp(path, "simt") == 0) enc->use_mma = 0;
     if (path && strcmp(path, "mma1") == 0) enc->use_mma = 1;
+    if (path && strcmp(path, "mma") == 0) enc->use_mma = 2;
+    enc->chunk = kChunkFused;
+    if (const char *c = getenv("EBSD_ENCODER_CHUNK")) {
+        const int v = atoi(c);
+        if (v >= 1 && v <= 4096) enc->chunk = v;
+    }
     for (int i = 1; i < EBSD_N_CONV; ++i) {
         const int cin = kPlan[i].cin, cout = kPlan[i].cout, kc = cin < 64 ? cin : 64;
         const int total = 9 * (cin / kc) * 2 * cout * kc;
@@ -485,6 +600,10 @@ size_t ebsd_encoder_workspace_bytes(const ebsd_encoder *enc, int64_t B) {
     if (B <= 0) return 0;
     const int chunk_cap = (enc && enc->use_mma) ? kChunkMma : kChunk;
     const size_t nimg = (size_t)(B < chunk_cap ? B : chunk_cap);
+    if (enc && enc->use_mma == 3) {
+        const size_t c = (size_t)(B < enc->chunk ? B : enc->chunk);
+        return carve_fused(nullptr, c).bytes + 1024;
+    }
     if (enc && enc->use_mma == 2) return carve_mma2(nullptr, nimg).bytes + 1024;
     // raw fp32 + (fp32 activations | fp16 hi + fp16 lo planes) + plane sums
     return nimg * (2 * kRawFloats * sizeof(float) + kSumsDoubles * sizeof(double)) + 256;
@@ -513,6 +632,18 @@ int ebsd_encoder_forward(ebsd_encoder *enc, const void *patterns, int dtype, int
     double *sums = (double *)(act + chunk * kRawFloats);
 
     const size_t px_bytes = dtype == EBSD_PATTERN_U8 ? 1 : 4;
+    if (enc->use_mma == 3) {
+        const size_t fchunk = (size_t)(B < enc->chunk ? B : enc->chunk);
+        const FusedWorkspace wf = carve_fused(workspace, fchunk);
+        for (int64_t b0 = 0; b0 < B; b0 += (int64_t)fchunk) {
+            const int nimg = (int)((B - b0) < (int64_t)fchunk ? (B - b0) : (int64_t)fchunk);
+            const void *pin = (const uint8_t *)patterns + (size_t)b0 * 128 * 128 * px_bytes;
+            if ((rc = forward_chunk_fused(enc, pin, dtype, nimg, fchunk, mu + b0 * 16,
+                                          logvar ? logvar + b0 * 16 : nullptr, wf, st)))
+                return rc;
+        }
+        return EBSD_OK;
+    }
     if (enc->use_mma == 2) {
         const Mma2Workspace w2 = carve_mma2(workspace, chunk);
         for (int64_t b0 = 0; b0 < B; b0 += kChunkMma) {
@@ -602,5 +733,22 @@ int ebsd_debug_conv_layer(ebsd_encoder *enc, int layer, int use_mma, const float
 }
 
 void ebsd_debug_set_flags(int flags) { g_debug_flags = flags; }
+
+int ebsd_debug_fused_layer(ebsd_encoder *enc, int layer, int dtype, const void *src, double *src_sums, int src_plane,
+                           int nimg, float *raw, double *sums, void *stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    EBSD_REQUIRE(enc && src && src_sums && raw && sums, "ebsd_debug_fused_layer: null pointer");
+    EBSD_REQUIRE(layer >= 1 && layer < EBSD_N_CONV, "ebsd_debug_fused_layer: layer must be in [1,9]");
+    EBSD_REQUIRE(nimg >= 1, "ebsd_debug_fused_layer: nimg must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    EBSD_CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)nimg * kPlan[layer].cout * 2 * sizeof(double), st));
+    if (layer == 1) {
+        EBSD_CUDA_TRY(cudaMemsetAsync(src_sums, 0, (size_t)nimg * 32 * 2 * sizeof(double), st));
+        if ((rc = conv0_stats(enc, src, dtype, nimg, src_sums, st))) return rc;
+        src_plane = 128 * 128;
+    }
+    return fused_dispatch(enc, layer, dtype, src, src_sums, src_plane, raw, sums, nimg, st);
+}
 
 }  // extern "C"

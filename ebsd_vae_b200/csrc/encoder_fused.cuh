@@ -1,0 +1,590 @@
+// K1, third generation: one kernel per convolution block that
+//   (1) BUILDS its own tensor-core operand in shared memory: "producer" warps read the previous block's raw fp32
+//       output (or, for the first tensor-core block, the uint8 pattern itself and run conv0 on CUDA cores), apply
+//       InstanceNorm + LeakyReLU(0.02) (latice/model.py:93-98) with the plane statistics the previous block left
+//       behind, split the result into fp16 hi / lo and store it in the swizzled K-major layout tcgen05.mma reads;
+//   (2) runs the 3x3 convolution as nine row-SHIFTED views of that window (implicit GEMM, three-term fp16 split,
+//       fp32 accumulation in TMEM, see encoder_mma.cuh for the arithmetic);
+//   (3) finishes in the epilogue warps: TMEM -> registers, plane statistics of the un-pooled output (sum, sum of
+//       squares, fp64 atomics), optional 2x2 max-pool with warp shuffles (pooling commutes with the increasing map
+//       x -> leaky((x-mean)*rstd), so it is applied to the raw values), raw fp32 NHWC store.
+// Nothing but the (pooled) raw output and 2 numbers per (image, channel) goes to memory between blocks: there are no
+// finisher kernels, no fp16 planes in HBM/L2 and no TMA window re-reads.
+//
+// Tile geometry.  A tile is 128 output positions = 16 groups of 8 horizontally adjacent pixels.  A UMMA K-major
+// operand is 16 eight-row groups at a constant stride (SBO), and tools/probe_umma_desc.cu shows that stride may be
+// any multiple of 16 bytes while the swizzle is applied to absolute shared-memory address bits.  So:
+//   * W >= 16: tile = 16 image rows x 8 columns.  The window is [18][8*NT + 2] positions (NT tiles side by side,
+//     1-pixel halo); group g of tile t under tap (dy,dx) starts at row (g + dy) * PITCH + 8 t + dx: stride PITCH.
+//   * W == 8:  tile = 2 images x 8 rows x 8 columns, window [10][2 images][10]; group j = 2 y + image starts at
+//     (y + dy) * 20 + image * 10 + dx = 10 j + ...: stride 10.
+// Zero padding is simply zeros the producers write at halo positions outside the image.
+//
+// Warp roles (384 threads): warp 0 weight TMA, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
+// (TMEM lane quarter = warp & 3), warps 8-11 producers.
+#pragma once
+#include "encoder_mma.cuh"
+
+namespace ebsd {
+
+enum FusedSrc { SRC_U8 = 0, SRC_F32 = 1, SRC_RAW = 2 };
+
+template <int CIN_, int COUT_, int W_, int SRC_>
+struct FusedCfg {
+    static constexpr int CIN = CIN_, COUT = COUT_, W = W_, SRC = SRC_;
+    static constexpr bool FIRST = SRC_ != SRC_RAW;           // conv0 is computed by the producers (CIN = 32, W = 128)
+    static constexpr int NI = W == 8 ? 2 : 1;                // images interleaved in one window row
+    static constexpr int NT = W >= 128 ? 4 : (W >= 64 ? 2 : 1);  // tiles per work item
+    static constexpr int TR = 16 / NI;                       // image rows per tile
+    static constexpr int WIN_H = TR + 2;
+    static constexpr int PITCH = NI == 1 ? 8 * NT + 2 : 10 * NI;
+    static constexpr int GSTRIDE = NI == 1 ? PITCH : 10;     // window rows between consecutive 8-row groups
+    static constexpr int WIN_POS = WIN_H * PITCH;
+    static constexpr int KC = CIN < 64 ? CIN : 64;
+    static constexpr int ROWB = KC * 2;
+    static constexpr int SWMASK = ROWB == 128 ? 7 : 3;
+    static constexpr int NCHUNK = CIN / KC;
+    static constexpr int KSTEPS = KC / 16;
+    static constexpr int A_PLANE = (WIN_POS * ROWB + 1023) / 1024 * 1024;
+    static constexpr int A_STAGE = 2 * A_PLANE;              // hi + lo
+    static constexpr int B_TILE = 2 * COUT * ROWB;           // [w_hi; w_lo] of one (tap, K chunk)
+    static constexpr bool RESIDENT_B = 9 * NCHUNK * B_TILE <= 80 * 1024;
+    static constexpr int A_STAGES = 2;
+    static constexpr int EXTRA = 8192;                       // barriers, tables, conv0 patch
+    static constexpr int B_FIT = (226 * 1024 - 1024 - EXTRA - A_STAGES * A_STAGE) / B_TILE;
+    static constexpr int B_STAGES = RESIDENT_B ? 9 * NCHUNK : (B_FIT > 6 ? 6 : B_FIT);
+    static constexpr int B_BYTES = B_STAGES * B_TILE;
+    static constexpr int ACC_COLS = NT * 2 * COUT;           // TMEM columns of one work item
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int SMEM_BYTES = 1024 + A_STAGES * A_STAGE + B_BYTES + EXTRA;
+    static constexpr int THREADS = 384;
+    static constexpr int ITEMS_X = NI == 1 ? W / (8 * NT) : 1;
+    static constexpr int ITEMS_PER_IMAGE = NI == 1 ? (W / 16) * ITEMS_X : 1;   // NI == 2: one item = 2 images
+    static_assert(2 * ACC_COLS <= TMEM_COLS, "TMEM budget");
+    static_assert(RESIDENT_B || B_STAGES >= 2, "weight ring does not fit");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(!FIRST || (CIN == 32 && W == 128), "conv0 fusion is for the 1->32->32 @128x128 front end");
+};
+
+struct FusedParams {
+    const void *src;         // SRC_RAW: fp32 [nimg,W,W,CIN] raw output of the previous block (pooled to this block's
+                             //          size); SRC_U8 / SRC_F32: patterns [nimg,128,128]
+    const double *src_sums;  // [nimg,CIN,2] plane sums (sum, sum of squares) of the block that produced src
+    double inv_src_plane;    // 1 / number of pixels those sums run over
+    const float *w0;         // FIRST: conv0 weights [tap][32] fp32
+    float *raw;              // out: fp32 [nimg,Wo,Wo,COUT], Wo = W/2 when pooling
+    double *sums;            // out: [nimg,COUT,2], must be zero on entry
+    int nimg;
+    int nitems;
+    int pool;
+};
+
+template <int ROWB, int GROUP_ROWS>
+__device__ __forceinline__ uint64_t umma_smem_desc_g(uint32_t saddr) {
+    constexpr uint64_t layout = ROWB == 128 ? 2ull : 4ull;
+    constexpr uint64_t sbo = ((uint64_t)GROUP_ROWS * ROWB) >> 4;
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// y = leaky(x * scale + shift) split into fp16 hi / lo; eight values -> two 16-byte chunks
+__device__ __forceinline__ void norm_split8(const float (&x)[8], const float2 *tab, uint4 &hi, uint4 &lo) {
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 t0 = tab[2 * j], t1 = tab[2 * j + 1];
+        float a = fmaf(x[2 * j], t0.x, t0.y), b = fmaf(x[2 * j + 1], t1.x, t1.y);
+        a = fmaxf(a, 0.02f * a);
+        b = fmaxf(b, 0.02f * b);
+        h[j] = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(h[j]);
+        l[j] = __floats2half2_rn(a - hf.x, b - hf.y);
+    }
+    hi = *(const uint4 *)h;
+    lo = *(const uint4 *)l;
+}
+
+template <class C>
+__device__ __forceinline__ void store_chunk(uint8_t *stage, uint32_t stage_u32, int pos, int c8, const uint4 &hi,
+                                            const uint4 &lo) {
+    const uint32_t a_hi = stage_u32 + pos * C::ROWB + c8 * 16;
+    const uint32_t a_lo = a_hi + C::A_PLANE;
+    const uint32_t s_hi = a_hi ^ (((a_hi >> 7) & C::SWMASK) << 4);
+    const uint32_t s_lo = a_lo ^ (((a_lo >> 7) & C::SWMASK) << 4);
+    *(uint4 *)(stage + (s_hi - stage_u32)) = hi;
+    *(uint4 *)(stage + (s_lo - stage_u32)) = lo;
+}
+
+template <int CIN, int COUT, int W, int SRC>
+__global__ void __launch_bounds__(384, 1)
+conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParams p) {
+    using C = FusedCfg<CIN, COUT, W, SRC>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem_b = smem + C::A_STAGES * C::A_STAGE;
+    uint8_t *extra = smem_b + C::B_BYTES;
+    uint64_t *a_full = (uint64_t *)extra;            // [A_STAGES]
+    uint64_t *a_empty = a_full + C::A_STAGES;        // [A_STAGES]
+    uint64_t *b_full = a_empty + C::A_STAGES;        // [B_STAGES] (<= 18)
+    uint64_t *b_empty = b_full + C::B_STAGES;        // [B_STAGES]
+    uint64_t *tfull_bar = b_empty + C::B_STAGES;     // [2]
+    uint64_t *tempty_bar = tfull_bar + 2;            // [2]
+    uint32_t *tmem_slot = (uint32_t *)(tempty_bar + 2);
+    float2 *tab = (float2 *)(extra + 512);           // [NI][CIN] (scale, shift) of the source planes: <= 2 KB
+    float *w0s = (float *)(extra + 2560);            // FIRST: [9][32] conv0 weights (1152 B)
+    float *patch = (float *)(extra + 3840);          // FIRST: [20][36] input pixels (2880 B)  -> ends at 6720
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::A_STAGES; ++s) {
+            mbar_init(&a_full[s], 128);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < C::B_STAGES; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull_bar[b], 1);
+            mbar_init(&tempty_bar[b], 4);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&map_w);
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // contiguous item range per CTA: consecutive items belong to the same image, so plane statistics are
+    // flushed once per image per warp instead of once per tile
+    const int per_cta = (p.nitems + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int item_begin = (int)blockIdx.x * per_cta;
+    const int item_end = item_begin + per_cta < p.nitems ? item_begin + per_cta : p.nitems;
+
+    if (warp == 0) {
+        // ===================== weight loads (TMA)
+        if (lane == 0) {
+            if (C::RESIDENT_B) {
+                for (int kb = 0; kb < 9 * C::NCHUNK; ++kb) {
+                    mbar_expect_tx(&b_full[kb], C::B_TILE);
+                    tma_load_2d(smem_b + kb * C::B_TILE, &map_w, 0, kb * 2 * COUT, &b_full[kb]);
+                }
+            } else {
+                unsigned bit = 0;
+                for (int item = item_begin; item < item_end; ++item)
+                    for (int cc = 0; cc < C::NCHUNK; ++cc)
+                        for (int tap = 0; tap < 9; ++tap, ++bit) {
+                            const int sb = bit % C::B_STAGES;
+                            mbar_wait_bounded(&b_empty[sb], ((bit / C::B_STAGES) & 1u) ^ 1u);
+                            mbar_expect_tx(&b_full[sb], C::B_TILE);
+                            tma_load_2d(smem_b + sb * C::B_TILE, &map_w, 0, (tap * C::NCHUNK + cc) * 2 * COUT,
+                                        &b_full[sb]);
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc_n2 = umma_idesc_f16(2 * COUT);
+            constexpr uint32_t idesc_n1 = umma_idesc_f16(COUT);
+            if (C::RESIDENT_B) {
+                for (int kb = 0; kb < 9 * C::NCHUNK; ++kb) mbar_wait_bounded(&b_full[kb], 0);
+                tc_fence_after();
+            }
+            unsigned ait = 0, bit = 0;
+            int j = 0;
+            for (int item = item_begin; item < item_end; ++item, ++j) {
+                const int buf = j & 1;
+                mbar_wait_bounded(&tempty_bar[buf], (((unsigned)j >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_item = tmem_base + (uint32_t)(buf * C::ACC_COLS);
+                for (int cc = 0; cc < C::NCHUNK; ++cc, ++ait) {
+                    const int sa = ait % C::A_STAGES;
+                    mbar_wait_bounded(&a_full[sa], (ait / C::A_STAGES) & 1u);
+                    tc_fence_after();
+                    const uint32_t win_hi = smem_u32(smem + sa * C::A_STAGE);
+                    const uint32_t win_lo = win_hi + C::A_PLANE;
+                    if (C::RESIDENT_B) {
+                        // all hi-plane MMAs (N = 2*COUT), then all lo-plane MMAs (N = COUT): two descriptor switches
+#pragma unroll 1
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int dy = tap / 3, dx = tap - dy * 3;
+                            const uint32_t shift = (uint32_t)((dy * C::PITCH + dx) * C::ROWB);
+                            const uint32_t b_w = smem_u32(smem_b + (tap * C::NCHUNK + cc) * C::B_TILE);
+#pragma unroll
+                            for (int t = 0; t < C::NT; ++t)
+#pragma unroll
+                                for (int k = 0; k < C::KSTEPS; ++k)
+                                    umma_f16(d_item + t * 2 * COUT,
+                                             umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_hi + shift + t * 8 * C::ROWB + k * 32),
+                                             umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_n2,
+                                             (cc | tap | k) != 0 ? 1u : 0u);
+                        }
+#pragma unroll 1
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int dy = tap / 3, dx = tap - dy * 3;
+                            const uint32_t shift = (uint32_t)((dy * C::PITCH + dx) * C::ROWB);
+                            const uint32_t b_w = smem_u32(smem_b + (tap * C::NCHUNK + cc) * C::B_TILE);
+#pragma unroll
+                            for (int t = 0; t < C::NT; ++t)
+#pragma unroll
+                                for (int k = 0; k < C::KSTEPS; ++k)
+                                    umma_f16(d_item + t * 2 * COUT,
+                                             umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_lo + shift + t * 8 * C::ROWB + k * 32),
+                                             umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_n1, 1u);
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int tap = 0; tap < 9; ++tap, ++bit) {
+                            const int dy = tap / 3, dx = tap - dy * 3;
+                            const uint32_t shift = (uint32_t)((dy * C::PITCH + dx) * C::ROWB);
+                            const int sb = bit % C::B_STAGES;
+                            mbar_wait_bounded(&b_full[sb], (bit / C::B_STAGES) & 1u);
+                            tc_fence_after();
+                            const uint32_t b_w = smem_u32(smem_b + sb * C::B_TILE);
+#pragma unroll
+                            for (int t = 0; t < C::NT; ++t)
+#pragma unroll
+                                for (int k = 0; k < C::KSTEPS; ++k)
+                                    umma_f16(d_item + t * 2 * COUT,
+                                             umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_hi + shift + t * 8 * C::ROWB + k * 32),
+                                             umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_n2,
+                                             (cc | tap | k) != 0 ? 1u : 0u);
+#pragma unroll
+                            for (int t = 0; t < C::NT; ++t)
+#pragma unroll
+                                for (int k = 0; k < C::KSTEPS; ++k)
+                                    umma_f16(d_item + t * 2 * COUT,
+                                             umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_lo + shift + t * 8 * C::ROWB + k * 32),
+                                             umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_n1, 1u);
+                            umma_commit(&b_empty[sb]);
+                        }
+                    }
+                    umma_commit(&a_empty[sa]);
+                }
+                umma_commit(&tfull_bar[buf]);
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== epilogue
+        const int quarter = warp & 3;
+        const int g = quarter * 4 + (lane >> 3);  // 8-row group of this lane inside the tile
+        const int xl = lane & 7;
+        constexpr int NCB = COUT / 32;
+        constexpr int PV = C::NI == 1 ? 8 : 16;   // lane distance of the vertical pooling partner
+        const int a_par = xl & 1;
+        const int b_par = C::NI == 1 ? (g & 1) : ((g >> 1) & 1);
+        const int im = C::NI == 1 ? 0 : (g & 1);  // image slot of this lane (NI == 2)
+        const int yl = C::NI == 1 ? g : (g >> 1); // image row of this lane relative to the tile
+        float acc1[NCB][C::NI], acc2[NCB][C::NI];
+#pragma unroll
+        for (int cb = 0; cb < NCB; ++cb)
+#pragma unroll
+            for (int s = 0; s < C::NI; ++s) acc1[cb][s] = acc2[cb][s] = 0.f;
+        int cur_n = -1;
+        auto flush = [&]() {
+            if (cur_n >= 0) {
+#pragma unroll
+                for (int s = 0; s < C::NI; ++s) {
+                    if (cur_n + s < p.nimg) {
+#pragma unroll
+                        for (int cb = 0; cb < NCB; ++cb) {
+                            double *dst = p.sums + ((long long)(cur_n + s) * COUT + cb * 32 + lane) * 2;
+                            atomicAdd(dst, (double)acc1[cb][s]);
+                            atomicAdd(dst + 1, (double)acc2[cb][s]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int cb = 0; cb < NCB; ++cb)
+#pragma unroll
+                for (int s = 0; s < C::NI; ++s) acc1[cb][s] = acc2[cb][s] = 0.f;
+        };
+        int j = 0;
+        for (int item = item_begin; item < item_end; ++item, ++j) {
+            const int buf = j & 1;
+            int n, y0, x0;
+            if (C::NI == 1) {
+                n = item / C::ITEMS_PER_IMAGE;
+                const int r = item - n * C::ITEMS_PER_IMAGE;
+                const int yb = r / C::ITEMS_X;
+                y0 = yb * 16;
+                x0 = (r - yb * C::ITEMS_X) * 8 * C::NT;
+            } else {
+                n = item * 2;
+                y0 = 0;
+                x0 = 0;
+            }
+            if (n != cur_n) {
+                flush();
+                cur_n = n;
+            }
+            const bool valid = n + im < p.nimg;
+            mbar_wait_bounded(&tfull_bar[buf], ((unsigned)j >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * C::ACC_COLS);
+#pragma unroll 1
+            for (int t = 0; t < C::NT; ++t) {
+                const int y = y0 + yl, x = x0 + 8 * t + xl;
+#pragma unroll
+                for (int cb = 0; cb < NCB; ++cb) {
+                    float v[32], w[32];
+                    tmem_ld32(t_row + t * 2 * COUT + cb * 32, v);
+                    tmem_ld32(t_row + t * 2 * COUT + COUT + cb * 32, w);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] + w[i] : 0.f;
+                    if (p.pool) {
+                        // transposing butterfly: after the x-pair step a lane keeps 16 channels, after the row-pair
+                        // step 8 channels, each the maximum over the 2x2 block
+                        float r[16], o[8];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float send = a_par ? v[i] : v[16 + i];
+                            const float keep = a_par ? v[16 + i] : v[i];
+                            r[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float send = b_par ? r[i] : r[8 + i];
+                            const float keep = b_par ? r[8 + i] : r[i];
+                            o[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, PV));
+                        }
+                        if (valid) {
+                            float *out = p.raw + ((((long long)(n + im) * (W / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * COUT +
+                                                  cb * 32 + a_par * 16 + b_par * 8);
+                            *(float4 *)out = make_float4(o[0], o[1], o[2], o[3]);
+                            *(float4 *)(out + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                        }
+                    } else if (valid) {
+                        float *out = p.raw + ((((long long)(n + im) * W + y) * W + x) * COUT + cb * 32);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            *(float4 *)(out + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    }
+                    // plane statistics of the un-pooled output
+                    if (C::NI == 1) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) w[i] = v[i] * v[i];
+                        acc1[cb][0] += warp_transpose_reduce32(v, lane);
+                        acc2[cb][0] += warp_transpose_reduce32(w, lane);
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < C::NI; ++s) {
+                            float a[32], b[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                a[i] = im == s ? v[i] : 0.f;
+                                b[i] = a[i] * a[i];
+                            }
+                            acc1[cb][s] += warp_transpose_reduce32(a, lane);
+                            acc2[cb][s] += warp_transpose_reduce32(b, lane);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+        flush();
+    } else if (warp >= 8) {
+        // ===================== producers: build the fp16 hi / lo window in shared memory
+        const int ptid = threadIdx.x - 256;
+        if (C::FIRST)
+            for (int i = ptid; i < 9 * 32; i += 128) w0s[i] = p.w0[i];
+        unsigned ait = 0;
+        int tab_n = -1;
+        for (int item = item_begin; item < item_end; ++item) {
+            int n, y0, x0;
+            if (C::NI == 1) {
+                n = item / C::ITEMS_PER_IMAGE;
+                const int r = item - n * C::ITEMS_PER_IMAGE;
+                const int yb = r / C::ITEMS_X;
+                y0 = yb * 16;
+                x0 = (r - yb * C::ITEMS_X) * 8 * C::NT;
+            } else {
+                n = item * 2;
+                y0 = 0;
+                x0 = 0;
+            }
+            if (n != tab_n) {
+                // (scale, shift) of the source planes: biased variance, eps = 1e-5 (torch instance_norm)
+                named_bar_sync(1, 128);
+                for (int i = ptid; i < C::NI * CIN; i += 128) {
+                    const int s = i / CIN, c = i - s * CIN;
+                    float2 t = make_float2(0.f, 0.f);
+                    if (n + s < p.nimg) {
+                        const double *q = p.src_sums + ((long long)(n + s) * CIN + c) * 2;
+                        const double mm = q[0] * p.inv_src_plane;
+                        double var = q[1] * p.inv_src_plane - mm * mm;
+                        if (var < 0.0) var = 0.0;
+                        const double rstd = 1.0 / sqrt(var + 1e-5);
+                        t = make_float2((float)rstd, (float)(-mm * rstd));
+                    }
+                    tab[i] = t;
+                }
+                tab_n = n;
+                named_bar_sync(1, 128);
+            }
+            if (C::FIRST) {
+                // stage the 20 x 36 input pixels this window needs (conv0 halo on top of the conv1 halo)
+                named_bar_sync(1, 128);
+                for (int i = ptid; i < 20 * 36; i += 128) {
+                    const int py = i / 36, px = i - py * 36;
+                    const int gy = y0 - 2 + py, gx = x0 - 2 + px;
+                    float v = 0.f;
+                    if (gy >= 0 && gy < 128 && gx >= 0 && gx < 128) {
+                        const long long off = ((long long)n * 128 + gy) * 128 + gx;
+                        if (SRC == SRC_U8) v = (float)((const uint8_t *)p.src)[off] / 255.0f;
+                        else v = ((const float *)p.src)[off];
+                    }
+                    patch[i] = v;
+                }
+                named_bar_sync(1, 128);
+            }
+            for (int cc = 0; cc < C::NCHUNK; ++cc, ++ait) {
+                const int sa = ait % C::A_STAGES;
+                mbar_wait_bounded(&a_empty[sa], ((ait / C::A_STAGES) & 1u) ^ 1u);
+                uint8_t *stage = smem + sa * C::A_STAGE;
+                const uint32_t stage_u32 = smem_u32(stage);
+                if (C::FIRST) {
+#pragma unroll 1
+                    for (int pos = ptid; pos < C::WIN_POS; pos += 128) {
+                        const int wy = pos / C::PITCH, wx = pos - wy * C::PITCH;
+                        const int y = y0 - 1 + wy, x = x0 - 1 + wx;
+                        if (y >= 0 && y < 128 && x >= 0 && x < 128) {
+                            float in[9];
+#pragma unroll
+                            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                                for (int dx = 0; dx < 3; ++dx) in[dy * 3 + dx] = patch[(wy + dy) * 36 + wx + dx];
+#pragma unroll
+                            for (int c8 = 0; c8 < 4; ++c8) {
+                                float acc[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+                                for (int tp = 0; tp < 9; ++tp) {
+                                    const float4 wa = *(const float4 *)(w0s + tp * 32 + c8 * 8);
+                                    const float4 wb = *(const float4 *)(w0s + tp * 32 + c8 * 8 + 4);
+                                    acc[0] = fmaf(in[tp], wa.x, acc[0]);
+                                    acc[1] = fmaf(in[tp], wa.y, acc[1]);
+                                    acc[2] = fmaf(in[tp], wa.z, acc[2]);
+                                    acc[3] = fmaf(in[tp], wa.w, acc[3]);
+                                    acc[4] = fmaf(in[tp], wb.x, acc[4]);
+                                    acc[5] = fmaf(in[tp], wb.y, acc[5]);
+                                    acc[6] = fmaf(in[tp], wb.z, acc[6]);
+                                    acc[7] = fmaf(in[tp], wb.w, acc[7]);
+                                }
+                                uint4 hi, lo;
+                                norm_split8(acc, tab + c8 * 8, hi, lo);
+                                store_chunk<C>(stage, stage_u32, pos, c8, hi, lo);
+                            }
+                        } else {
+                            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                            for (int c8 = 0; c8 < 4; ++c8) store_chunk<C>(stage, stage_u32, pos, c8, z, z);
+                        }
+                    }
+                } else {
+                    constexpr int C8 = C::KC / 8;
+                    constexpr int UNITS = C::WIN_POS * C8;
+#pragma unroll 2
+                    for (int u = ptid; u < UNITS; u += 128) {
+                        const int pos = u / C8, c8 = u - pos * C8;
+                        const int wy = pos / C::PITCH, wx = pos - wy * C::PITCH;
+                        int nn, y, x, s;
+                        if (C::NI == 1) {
+                            s = 0;
+                            nn = n;
+                            y = y0 - 1 + wy;
+                            x = x0 - 1 + wx;
+                        } else {
+                            s = wx / 10;
+                            nn = n + s;
+                            y = wy - 1;
+                            x = wx - s * 10 - 1;
+                        }
+                        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+                        if (y >= 0 && y < W && x >= 0 && x < W && nn < p.nimg) {
+                            const float *src = (const float *)p.src + ((((long long)nn * W + y) * W + x) * CIN + cc * C::KC + c8 * 8);
+                            const float4 fa = __ldg((const float4 *)src), fb = __ldg((const float4 *)src + 1);
+                            const float xv[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
+                            norm_split8(xv, tab + s * CIN + cc * C::KC + c8 * 8, hi, lo);
+                        }
+                        store_chunk<C>(stage, stage_u32, pos, c8, hi, lo);
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&a_full[sa]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// mu / logvar heads (latice/model.py:57-58, 127-129) straight from the last block's pooled raw output
+// raw9 [n,4,4,128] + its plane sums (64 pixels): InstanceNorm + LeakyReLU here, then the two 2048 -> 16 products.
+__global__ void __launch_bounds__(256) heads_norm_kernel(const float *__restrict__ raw9, const double *__restrict__ sums9,
+                                                         const float *__restrict__ wh, const float *__restrict__ bh,
+                                                         float *__restrict__ mu, float *__restrict__ logvar) {
+    __shared__ float feat[2048];
+    __shared__ float2 tb[128];
+    const long long n = blockIdx.x;
+    if (threadIdx.x < 128) {
+        const double *q = sums9 + (n * 128 + threadIdx.x) * 2;
+        const double mm = q[0] * (1.0 / 64.0);
+        double var = q[1] * (1.0 / 64.0) - mm * mm;
+        if (var < 0.0) var = 0.0;
+        const double rstd = 1.0 / sqrt(var + 1e-5);
+        tb[threadIdx.x] = make_float2((float)rstd, (float)(-mm * rstd));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2048; i += 256) {
+        const float2 t = tb[i & 127];
+        const float a = fmaf(raw9[n * 2048 + i], t.x, t.y);
+        feat[i] = fmaxf(a, 0.02f * a);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4 *f = (const float4 *)feat;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = lane; i < 512; i += 32) {
+        const float4 x = f[i];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const float4 w = ((const float4 *)(wh + (warp * 4 + o) * 2048))[i];
+            acc[o] = fmaf(x.x, w.x, acc[o]);
+            acc[o] = fmaf(x.y, w.y, acc[o]);
+            acc[o] = fmaf(x.z, w.z, acc[o]);
+            acc[o] = fmaf(x.w, w.w, acc[o]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int oi = warp * 4 + o;
+            const float v = acc[o] + bh[oi];
+            if (oi < 16) mu[n * 16 + oi] = v;
+            else if (logvar) logvar[n * 16 + (oi - 16)] = v;
+        }
+    }
+}
+
+}  // namespace ebsd

@@ -80,6 +80,14 @@ int ebsd_encoder_forward(ebsd_encoder *enc, const void *patterns, int dtype, int
 int ebsd_debug_conv_layer(ebsd_encoder *enc, int layer, int use_mma, const float *act, int nimg, float *raw,
                           double *sums, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Test hook for the fused blocks (encoder_fused.cuh): run block `layer` (1..9) alone.
+ * layer 1: src = patterns [nimg,128,128] (dtype EBSD_PATTERN_*); src_sums [nimg,32,2] is scratch (conv0 statistics).
+ * layers 2..9: src = raw fp32 NHWC [nimg,W,W,Cin] and src_sums [nimg,Cin,2] its plane sums over src_plane pixels;
+ * the block applies InstanceNorm + LeakyReLU to src, convolves, and returns raw [nimg,Wo,Wo,Cout] (2x2 max-pooled
+ * for layers 1,3,5,7,9) plus the plane sums [nimg,Cout,2] of the un-pooled output. */
+int ebsd_debug_fused_layer(ebsd_encoder *enc, int layer, int dtype, const void *src, double *src_sums, int src_plane,
+                           int nimg, float *raw, double *sums, void *stream);
+
 /* Profiling hook: switches parts of the shifted-window conv kernel off (results are then wrong). 0 = normal. */
 void ebsd_debug_set_flags(int flags);
 

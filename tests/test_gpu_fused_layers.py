@@ -1,0 +1,95 @@
+"""GPU parity, block by block, of the fused producer / tcgen05 / epilogue kernels (csrc/encoder_fused.cuh):
+InstanceNorm + LeakyReLU of the incoming raw planes, 3x3 convolution, optional 2x2 max-pool of the raw output and the
+plane sums of the un-pooled output -- against torch float64 on the same inputs (latice/model.py:93-125)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import encoder_ref as R
+
+pytestmark = pytest.mark.gpu
+
+PLAN = {1: (32, 32, 128, True), 2: (32, 64, 64, False), 3: (64, 64, 64, True), 4: (64, 128, 32, False),
+        5: (128, 128, 32, True), 6: (128, 128, 16, False), 7: (128, 128, 16, True), 8: (128, 128, 8, False),
+        9: (128, 128, 8, True)}
+IDX = {0: 0, 1: 1, 2: 3, 3: 4, 4: 6, 5: 7, 6: 9, 7: 10, 8: 12, 9: 13}
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import ebsd_vae_b200 as E
+    sd = R.make_state_dict(42)
+    return E.EncoderEngine(sd, "cuda"), sd
+
+
+def _block_input(x):
+    """InstanceNorm (biased variance, eps 1e-5) + LeakyReLU(0.02) in float64."""
+    m = x.mean(dim=(2, 3), keepdim=True)
+    v = x.var(dim=(2, 3), unbiased=False, keepdim=True)
+    y = (x - m) / torch.sqrt(v + 1e-5)
+    return torch.where(y > 0, y, 0.02 * y)
+
+
+def _run(eng, layer, dtype, src, src_sums, src_plane, nimg):
+    from ebsd_vae_b200 import _native
+    lib = _native.load()
+    cin, cout, hw, pool = PLAN[layer]
+    ho = hw // 2 if pool else hw
+    raw = torch.full((nimg, ho, ho, cout), float("nan"), dtype=torch.float32, device="cuda")
+    sums = torch.zeros((nimg, cout, 2), dtype=torch.float64, device="cuda")
+    _native.check(lib.ebsd_debug_fused_layer(eng._handle, layer, dtype, src.data_ptr(), src_sums.data_ptr(), src_plane,
+                                             nimg, raw.data_ptr(), sums.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "ebsd_debug_fused_layer")
+    torch.cuda.synchronize()
+    return raw, sums
+
+
+def _check(layer, nimg, raw, sums, want_conv, pool):
+    cin, cout, hw, _ = PLAN[layer]
+    want = F.max_pool2d(want_conv, 2) if pool else want_conv
+    want = want.permute(0, 2, 3, 1).contiguous()
+    got = raw.cpu().double()
+    assert torch.isfinite(got).all(), "kernel left part of the output unwritten"
+    scale = want_conv.abs().max().item()
+    err = (got - want).abs().max().item() / scale
+    print(f"fused layer {layer} nimg {nimg}: max err / max |y| = {err:.3e}")
+    assert err < 2e-5
+    s1 = want_conv.sum(dim=(2, 3))
+    s2 = (want_conv * want_conv).sum(dim=(2, 3))
+    np.testing.assert_allclose(sums[:, :, 0].cpu().numpy(), s1.numpy(), rtol=0, atol=2e-5 * scale * hw * hw)
+    np.testing.assert_allclose(sums[:, :, 1].cpu().numpy(), s2.numpy(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("layer,nimg", [(2, 1), (2, 3), (3, 2), (4, 5), (5, 3), (6, 7), (7, 16), (8, 1), (8, 5), (9, 2),
+                                        (9, 37), (3, 40)])
+def test_fused_block_matches_torch(engine, layer, nimg):
+    eng, sd = engine
+    cin, cout, hw, pool = PLAN[layer]
+    g = torch.Generator().manual_seed(7000 * layer + nimg)
+    x = (torch.randn((nimg, cin, hw, hw), generator=g) * 1.7 + 0.3).float()   # raw planes of the previous block
+    xd = x.double()
+    w = sd[f"encoder.{IDX[layer]}.0.weight"].double()
+    want_conv = F.conv2d(_block_input(xd), w, None, padding=1)
+    src = x.permute(0, 2, 3, 1).contiguous().cuda()
+    src_sums = torch.stack([xd.sum(dim=(2, 3)), (xd * xd).sum(dim=(2, 3))], dim=2).contiguous().cuda()
+    raw, sums = _run(eng, layer, 0, src, src_sums, hw * hw, nimg)
+    _check(layer, nimg, raw, sums, want_conv, pool)
+
+
+@pytest.mark.parametrize("nimg,dtype", [(1, 0), (3, 0), (2, 1)])
+def test_fused_front_end_matches_torch(engine, nimg, dtype):
+    """conv0 (CUDA cores, inside the producers) + conv1 (tensor cores) + pooling, from the uint8 / float32 pattern."""
+    eng, sd = engine
+    pats = R.synthetic_patterns(nimg, seed=11 + nimg)                    # uint8 [n,128,128]
+    x_in = (pats.double() / 255.0).unsqueeze(1)
+    w0 = sd["encoder.0.0.weight"].double()
+    w1 = sd["encoder.1.0.weight"].double()
+    want_conv = F.conv2d(_block_input(F.conv2d(x_in, w0, None, padding=1)), w1, None, padding=1)
+    if dtype == 0:
+        src = pats.contiguous().cuda()
+    else:
+        src = (pats.float() / 255.0).contiguous().cuda()
+    scratch = torch.zeros((nimg, 32, 2), dtype=torch.float64, device="cuda")
+    raw, sums = _run(eng, 1, dtype, src, scratch, 128 * 128, nimg)
+    _check(1, nimg, raw, sums, want_conv, True)
