@@ -452,6 +452,7 @@ int launch_fused(const ebsd_encoder *enc, int layer, const void *src, const doub
     p.nimg = nimg;
     p.nitems = C::NI == 1 ? nimg * C::ITEMS_PER_IMAGE : (nimg + C::NI - 1) / C::NI;
     p.pool = pool ? 1 : 0;
+    p.dbg = g_debug_flags;
     const int sms = sm_count();
     const int per = (p.nitems + sms - 1) / sms;
     const int grid = (p.nitems + per - 1) / per;

@@ -20,8 +20,8 @@
 //     (y + dy) * 20 + image * 10 + dx = 10 j + ...: stride 10.
 // Zero padding is simply zeros the producers write at halo positions outside the image.
 //
-// Warp roles (384 threads): warp 0 weight TMA, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
-// (TMEM lane quarter = warp & 3), warps 8-11 producers.
+// Warp roles (512 threads): warp 0 weight TMA, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
+// (TMEM lane quarter = warp & 3), warps 8-15 producers (two per scheduler: global-load and ALU latency overlap).
 #pragma once
 #include "encoder_mma.cuh"
 
@@ -57,7 +57,8 @@ struct FusedCfg {
     static constexpr int ACC_COLS = NT * 2 * COUT;           // TMEM columns of one work item
     static constexpr int TMEM_COLS = 512;
     static constexpr int SMEM_BYTES = 1024 + A_STAGES * A_STAGE + B_BYTES + EXTRA;
-    static constexpr int THREADS = 384;
+    static constexpr int THREADS = 512;
+    static constexpr int PRODUCERS = 256;                    // producer threads (warps 8..15)
     static constexpr int ITEMS_X = NI == 1 ? W / (8 * NT) : 1;
     static constexpr int ITEMS_PER_IMAGE = NI == 1 ? (W / 16) * ITEMS_X : 1;   // NI == 2: one item = 2 images
     static_assert(2 * ACC_COLS <= TMEM_COLS, "TMEM budget");
@@ -77,6 +78,8 @@ struct FusedParams {
     int nimg;
     int nitems;
     int pool;
+    int dbg;                 // profiling switches (ebsd_debug_set_flags): 1 producers write nothing, 2 no MMAs,
+                             // 4 epilogue does nothing but release TMEM, 8 no plane statistics, 16 no stores
 };
 
 template <int ROWB, int GROUP_ROWS>
@@ -90,12 +93,36 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// y = leaky(x * scale + shift) split into fp16 hi / lo; eight values -> two 16-byte chunks
-__device__ __forceinline__ void norm_split8(const float (&x)[8], const float2 *tab, uint4 &hi, uint4 &lo) {
+// Shared-memory accesses by 32-bit shared-window address: pointers derived from the aligned dynamic-smem base lose
+// their address space and would compile to generic LD/ST with 64-bit address arithmetic.
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// y = leaky(x * scale + shift) split into fp16 hi / lo; eight values -> two 16-byte chunks.
+// tab_u32: shared address of eight (scale, shift) pairs.
+__device__ __forceinline__ void norm_split8(const float (&x)[8], uint32_t tab_u32, uint4 &hi, uint4 &lo) {
     __half2 h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float2 t0 = tab[2 * j], t1 = tab[2 * j + 1];
+        const float4 tt = lds128(tab_u32 + j * 16);
+        const float2 t0 = make_float2(tt.x, tt.y), t1 = make_float2(tt.z, tt.w);
         float a = fmaf(x[2 * j], t0.x, t0.y), b = fmaf(x[2 * j + 1], t1.x, t1.y);
         a = fmaxf(a, 0.02f * a);
         b = fmaxf(b, 0.02f * b);
@@ -108,18 +135,15 @@ __device__ __forceinline__ void norm_split8(const float (&x)[8], const float2 *t
 }
 
 template <class C>
-__device__ __forceinline__ void store_chunk(uint8_t *stage, uint32_t stage_u32, int pos, int c8, const uint4 &hi,
-                                            const uint4 &lo) {
+__device__ __forceinline__ void store_chunk(uint32_t stage_u32, int pos, int c8, const uint4 &hi, const uint4 &lo) {
     const uint32_t a_hi = stage_u32 + pos * C::ROWB + c8 * 16;
     const uint32_t a_lo = a_hi + C::A_PLANE;
-    const uint32_t s_hi = a_hi ^ (((a_hi >> 7) & C::SWMASK) << 4);
-    const uint32_t s_lo = a_lo ^ (((a_lo >> 7) & C::SWMASK) << 4);
-    *(uint4 *)(stage + (s_hi - stage_u32)) = hi;
-    *(uint4 *)(stage + (s_lo - stage_u32)) = lo;
+    sts128(a_hi ^ (((a_hi >> 7) & C::SWMASK) << 4), hi);
+    sts128(a_lo ^ (((a_lo >> 7) & C::SWMASK) << 4), lo);
 }
 
 template <int CIN, int COUT, int W, int SRC>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(512, 1)
 conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParams p) {
     using C = FusedCfg<CIN, COUT, W, SRC>;
     extern __shared__ uint8_t smem_raw[];
@@ -133,16 +157,16 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
     uint64_t *tfull_bar = b_empty + C::B_STAGES;     // [2]
     uint64_t *tempty_bar = tfull_bar + 2;            // [2]
     uint32_t *tmem_slot = (uint32_t *)(tempty_bar + 2);
-    float2 *tab = (float2 *)(extra + 512);           // [NI][CIN] (scale, shift) of the source planes: <= 2 KB
-    float *w0s = (float *)(extra + 2560);            // FIRST: [9][32] conv0 weights (1152 B)
-    float *patch = (float *)(extra + 3840);          // FIRST: [20][36] input pixels (2880 B)  -> ends at 6720
+    const uint32_t tab_u32 = smem_u32(extra + 512);     // float2 [NI][CIN] (scale, shift) of the source planes: <= 2 KB
+    const uint32_t w0s_u32 = smem_u32(extra + 2560);    // FIRST: float [9][32] conv0 weights (1152 B)
+    const uint32_t patch_u32 = smem_u32(extra + 3840);  // FIRST: float [20][36] input pixels (2880 B) -> ends at 6720
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::A_STAGES; ++s) {
-            mbar_init(&a_full[s], 128);
+            mbar_init(&a_full[s], C::PRODUCERS);
             mbar_init(&a_empty[s], 1);
         }
         for (int s = 0; s < C::B_STAGES; ++s) {
@@ -170,7 +194,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
 
     if (warp == 0) {
         // ===================== weight loads (TMA)
-        if (lane == 0) {
+        if (elect_one_sync()) {
             if (C::RESIDENT_B) {
                 for (int kb = 0; kb < 9 * C::NCHUNK; ++kb) {
                     mbar_expect_tx(&b_full[kb], C::B_TILE);
@@ -191,7 +215,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
         }
     } else if (warp == 1) {
         // ===================== MMA issuer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc_n2 = umma_idesc_f16(2 * COUT);
             constexpr uint32_t idesc_n1 = umma_idesc_f16(COUT);
             if (C::RESIDENT_B) {
@@ -222,7 +246,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
                             for (int t = 0; t < C::NT; ++t)
 #pragma unroll
                                 for (int k = 0; k < C::KSTEPS; ++k)
-                                    umma_f16(d_item + t * 2 * COUT,
+                                    if (!(p.dbg & 2)) umma_f16(d_item + t * 2 * COUT,
                                              umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_hi + shift + t * 8 * C::ROWB + k * 32),
                                              umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_n2,
                                              (cc | tap | k) != 0 ? 1u : 0u);
@@ -236,7 +260,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
                             for (int t = 0; t < C::NT; ++t)
 #pragma unroll
                                 for (int k = 0; k < C::KSTEPS; ++k)
-                                    umma_f16(d_item + t * 2 * COUT,
+                                    if (!(p.dbg & 2)) umma_f16(d_item + t * 2 * COUT,
                                              umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_lo + shift + t * 8 * C::ROWB + k * 32),
                                              umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_n1, 1u);
                         }
@@ -253,7 +277,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
                             for (int t = 0; t < C::NT; ++t)
 #pragma unroll
                                 for (int k = 0; k < C::KSTEPS; ++k)
-                                    umma_f16(d_item + t * 2 * COUT,
+                                    if (!(p.dbg & 2)) umma_f16(d_item + t * 2 * COUT,
                                              umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_hi + shift + t * 8 * C::ROWB + k * 32),
                                              umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_n2,
                                              (cc | tap | k) != 0 ? 1u : 0u);
@@ -261,7 +285,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
                             for (int t = 0; t < C::NT; ++t)
 #pragma unroll
                                 for (int k = 0; k < C::KSTEPS; ++k)
-                                    umma_f16(d_item + t * 2 * COUT,
+                                    if (!(p.dbg & 2)) umma_f16(d_item + t * 2 * COUT,
                                              umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_lo + shift + t * 8 * C::ROWB + k * 32),
                                              umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_n1, 1u);
                             umma_commit(&b_empty[sb]);
@@ -332,7 +356,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * C::ACC_COLS);
 #pragma unroll 1
-            for (int t = 0; t < C::NT; ++t) {
+            for (int t = 0; t < ((p.dbg & 4) ? 0 : C::NT); ++t) {
                 const int y = y0 + yl, x = x0 + 8 * t + xl;
 #pragma unroll
                 for (int cb = 0; cb < NCB; ++cb) {
@@ -358,19 +382,20 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
                             const float keep = b_par ? r[8 + i] : r[i];
                             o[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, PV));
                         }
-                        if (valid) {
+                        if (valid && !(p.dbg & 16)) {
                             float *out = p.raw + ((((long long)(n + im) * (W / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * COUT +
                                                   cb * 32 + a_par * 16 + b_par * 8);
                             *(float4 *)out = make_float4(o[0], o[1], o[2], o[3]);
                             *(float4 *)(out + 4) = make_float4(o[4], o[5], o[6], o[7]);
                         }
-                    } else if (valid) {
+                    } else if (valid && !(p.dbg & 16)) {
                         float *out = p.raw + ((((long long)(n + im) * W + y) * W + x) * COUT + cb * 32);
 #pragma unroll
                         for (int i = 0; i < 32; i += 4)
                             *(float4 *)(out + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                     }
                     // plane statistics of the un-pooled output
+                    if (p.dbg & 8) continue;
                     if (C::NI == 1) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) w[i] = v[i] * v[i];
@@ -399,12 +424,8 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
     } else if (warp >= 8) {
         // ===================== producers: build the fp16 hi / lo window in shared memory
         const int ptid = threadIdx.x - 256;
-        if (C::FIRST)
-            for (int i = ptid; i < 9 * 32; i += 128) w0s[i] = p.w0[i];
-        unsigned ait = 0;
-        int tab_n = -1;
-        for (int item = item_begin; item < item_end; ++item) {
-            int n, y0, x0;
+        const uint32_t smem_base_u32 = smem_u32(smem);
+        auto decode = [&](int item, int &n, int &y0, int &x0) {
             if (C::NI == 1) {
                 n = item / C::ITEMS_PER_IMAGE;
                 const int r = item - n * C::ITEMS_PER_IMAGE;
@@ -416,116 +437,215 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
                 y0 = 0;
                 x0 = 0;
             }
-            if (n != tab_n) {
-                // (scale, shift) of the source planes: biased variance, eps = 1e-5 (torch instance_norm)
-                named_bar_sync(1, 128);
-                for (int i = ptid; i < C::NI * CIN; i += 128) {
-                    const int s = i / CIN, c = i - s * CIN;
-                    float2 t = make_float2(0.f, 0.f);
-                    if (n + s < p.nimg) {
-                        const double *q = p.src_sums + ((long long)(n + s) * CIN + c) * 2;
-                        const double mm = q[0] * p.inv_src_plane;
-                        double var = q[1] * p.inv_src_plane - mm * mm;
-                        if (var < 0.0) var = 0.0;
-                        const double rstd = 1.0 / sqrt(var + 1e-5);
-                        t = make_float2((float)rstd, (float)(-mm * rstd));
-                    }
-                    tab[i] = t;
+        };
+        int tab_n = -1;
+        // (scale, shift) of the source planes: biased variance, eps = 1e-5 (torch instance_norm)
+        auto update_table = [&](int n) {
+            if (n == tab_n) return;
+            named_bar_sync(1, C::PRODUCERS);
+            for (int i = ptid; i < C::NI * CIN; i += C::PRODUCERS) {
+                const int s = i / CIN, c = i - s * CIN;
+                float2 t = make_float2(0.f, 0.f);
+                if (n + s < p.nimg) {
+                    const double *q = p.src_sums + ((long long)(n + s) * CIN + c) * 2;
+                    const double mm = q[0] * p.inv_src_plane;
+                    double var = q[1] * p.inv_src_plane - mm * mm;
+                    if (var < 0.0) var = 0.0;
+                    const double rstd = 1.0 / sqrt(var + 1e-5);
+                    t = make_float2((float)rstd, (float)(-mm * rstd));
                 }
-                tab_n = n;
-                named_bar_sync(1, 128);
+                sts64(tab_u32 + i * 8, t);
             }
-            if (C::FIRST) {
-                // stage the 20 x 36 input pixels this window needs (conv0 halo on top of the conv1 halo)
-                named_bar_sync(1, 128);
-                for (int i = ptid; i < 20 * 36; i += 128) {
-                    const int py = i / 36, px = i - py * 36;
+            tab_n = n;
+            named_bar_sync(1, C::PRODUCERS);
+        };
+        unsigned ait = 0;
+        if constexpr (C::FIRST) {
+            for (int i = ptid; i < 9 * 32; i += C::PRODUCERS) sts32(w0s_u32 + i * 4, __float_as_uint(p.w0[i]));
+            // the 20 x 36 input pixels of a window (conv0 halo on top of the conv1 halo) are fetched one item ahead
+            constexpr int NPV = (20 * 36 + C::PRODUCERS - 1) / C::PRODUCERS;
+            uint32_t pv[NPV];  // raw pixel bits; converted when they are written to the patch, one item later
+            auto load_patch = [&](int item) {
+                int n, y0, x0;
+                decode(item, n, y0, x0);
+#pragma unroll
+                for (int i = 0; i < NPV; ++i) {
+                    const int idx = ptid + C::PRODUCERS * i;
+                    const int py = idx / 36, px = idx - py * 36;
                     const int gy = y0 - 2 + py, gx = x0 - 2 + px;
-                    float v = 0.f;
-                    if (gy >= 0 && gy < 128 && gx >= 0 && gx < 128) {
+                    uint32_t v = 0u;
+                    if (idx < 20 * 36 && gy >= 0 && gy < 128 && gx >= 0 && gx < 128) {
                         const long long off = ((long long)n * 128 + gy) * 128 + gx;
-                        if (SRC == SRC_U8) v = (float)((const uint8_t *)p.src)[off] / 255.0f;
-                        else v = ((const float *)p.src)[off];
+                        if (SRC == SRC_U8) v = __ldg((const uint8_t *)p.src + off);
+                        else v = __float_as_uint(__ldg((const float *)p.src + off));
                     }
-                    patch[i] = v;
+                    pv[i] = v;
                 }
-                named_bar_sync(1, 128);
-            }
-            for (int cc = 0; cc < C::NCHUNK; ++cc, ++ait) {
+            };
+            if (item_begin < item_end) load_patch(item_begin);
+            for (int item = item_begin; item < item_end; ++item, ++ait) {
+                int n, y0, x0;
+                decode(item, n, y0, x0);
+                update_table(n);
+                named_bar_sync(1, C::PRODUCERS);
+#pragma unroll
+                for (int i = 0; i < NPV; ++i)
+                    if (ptid + C::PRODUCERS * i < 20 * 36) {
+                        // ToTensor: uint8 -> float32, true division by 255 (latice/data_module.py:31)
+                        const float v = SRC == SRC_U8 ? (float)pv[i] / 255.0f : __uint_as_float(pv[i]);
+                        sts32(patch_u32 + (ptid + C::PRODUCERS * i) * 4, __float_as_uint(v));
+                    }
+                named_bar_sync(1, C::PRODUCERS);
+                if (item + 1 < item_end) load_patch(item + 1);
                 const int sa = ait % C::A_STAGES;
                 mbar_wait_bounded(&a_empty[sa], ((ait / C::A_STAGES) & 1u) ^ 1u);
-                uint8_t *stage = smem + sa * C::A_STAGE;
-                const uint32_t stage_u32 = smem_u32(stage);
-                if (C::FIRST) {
+                const uint32_t stage_u32 = smem_base_u32 + sa * C::A_STAGE;
 #pragma unroll 1
-                    for (int pos = ptid; pos < C::WIN_POS; pos += 128) {
-                        const int wy = pos / C::PITCH, wx = pos - wy * C::PITCH;
-                        const int y = y0 - 1 + wy, x = x0 - 1 + wx;
-                        if (y >= 0 && y < 128 && x >= 0 && x < 128) {
-                            float in[9];
+                for (int pos = ptid; pos < ((p.dbg & 1) ? 0 : C::WIN_POS); pos += C::PRODUCERS) {
+                    const int wy = pos / C::PITCH, wx = pos - wy * C::PITCH;
+                    const int y = y0 - 1 + wy, x = x0 - 1 + wx;
+                    if (y >= 0 && y < 128 && x >= 0 && x < 128) {
+                        float in[9];
 #pragma unroll
-                            for (int dy = 0; dy < 3; ++dy)
+                        for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                                for (int dx = 0; dx < 3; ++dx) in[dy * 3 + dx] = patch[(wy + dy) * 36 + wx + dx];
+                            for (int dx = 0; dx < 3; ++dx)
+                                in[dy * 3 + dx] = lds32(patch_u32 + ((wy + dy) * 36 + wx + dx) * 4);
 #pragma unroll
-                            for (int c8 = 0; c8 < 4; ++c8) {
-                                float acc[8];
+                        for (int c16 = 0; c16 < 2; ++c16) {
+                            float acc[16];
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+                            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
 #pragma unroll
-                                for (int tp = 0; tp < 9; ++tp) {
-                                    const float4 wa = *(const float4 *)(w0s + tp * 32 + c8 * 8);
-                                    const float4 wb = *(const float4 *)(w0s + tp * 32 + c8 * 8 + 4);
-                                    acc[0] = fmaf(in[tp], wa.x, acc[0]);
-                                    acc[1] = fmaf(in[tp], wa.y, acc[1]);
-                                    acc[2] = fmaf(in[tp], wa.z, acc[2]);
-                                    acc[3] = fmaf(in[tp], wa.w, acc[3]);
-                                    acc[4] = fmaf(in[tp], wb.x, acc[4]);
-                                    acc[5] = fmaf(in[tp], wb.y, acc[5]);
-                                    acc[6] = fmaf(in[tp], wb.z, acc[6]);
-                                    acc[7] = fmaf(in[tp], wb.w, acc[7]);
+                            for (int tp = 0; tp < 9; ++tp) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float4 wv = lds128(w0s_u32 + (tp * 32 + c16 * 16 + q * 4) * 4);
+                                    acc[q * 4 + 0] = fmaf(in[tp], wv.x, acc[q * 4 + 0]);
+                                    acc[q * 4 + 1] = fmaf(in[tp], wv.y, acc[q * 4 + 1]);
+                                    acc[q * 4 + 2] = fmaf(in[tp], wv.z, acc[q * 4 + 2]);
+                                    acc[q * 4 + 3] = fmaf(in[tp], wv.w, acc[q * 4 + 3]);
                                 }
-                                uint4 hi, lo;
-                                norm_split8(acc, tab + c8 * 8, hi, lo);
-                                store_chunk<C>(stage, stage_u32, pos, c8, hi, lo);
                             }
-                        } else {
-                            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                            for (int c8 = 0; c8 < 4; ++c8) store_chunk<C>(stage, stage_u32, pos, c8, z, z);
+                            for (int h8 = 0; h8 < 2; ++h8) {
+                                const float a8[8] = {acc[h8 * 8 + 0], acc[h8 * 8 + 1], acc[h8 * 8 + 2], acc[h8 * 8 + 3],
+                                                     acc[h8 * 8 + 4], acc[h8 * 8 + 5], acc[h8 * 8 + 6], acc[h8 * 8 + 7]};
+                                uint4 hi, lo;
+                                norm_split8(a8, tab_u32 + (c16 * 2 + h8) * 64, hi, lo);
+                                store_chunk<C>(stage_u32, pos, c16 * 2 + h8, hi, lo);
+                            }
                         }
-                    }
-                } else {
-                    constexpr int C8 = C::KC / 8;
-                    constexpr int UNITS = C::WIN_POS * C8;
-#pragma unroll 2
-                    for (int u = ptid; u < UNITS; u += 128) {
-                        const int pos = u / C8, c8 = u - pos * C8;
-                        const int wy = pos / C::PITCH, wx = pos - wy * C::PITCH;
-                        int nn, y, x, s;
-                        if (C::NI == 1) {
-                            s = 0;
-                            nn = n;
-                            y = y0 - 1 + wy;
-                            x = x0 - 1 + wx;
-                        } else {
-                            s = wx / 10;
-                            nn = n + s;
-                            y = wy - 1;
-                            x = wx - s * 10 - 1;
-                        }
-                        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-                        if (y >= 0 && y < W && x >= 0 && x < W && nn < p.nimg) {
-                            const float *src = (const float *)p.src + ((((long long)nn * W + y) * W + x) * CIN + cc * C::KC + c8 * 8);
-                            const float4 fa = __ldg((const float4 *)src), fb = __ldg((const float4 *)src + 1);
-                            const float xv[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
-                            norm_split8(xv, tab + s * CIN + cc * C::KC + c8 * 8, hi, lo);
-                        }
-                        store_chunk<C>(stage, stage_u32, pos, c8, hi, lo);
+                    } else {
+                        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                        for (int c8 = 0; c8 < 4; ++c8) store_chunk<C>(stage_u32, pos, c8, z, z);
                     }
                 }
                 fence_proxy_async();
                 mbar_arrive(&a_full[sa]);
+            }
+        } else {
+            // raw fp32 -> normalise -> LeakyReLU -> fp16 hi / lo.  One unit = 8 channels of one window position; the
+            // global loads of the next batch of units are in flight while the current batch is converted, across
+            // stage and item boundaries (a stage = one K chunk of one window).
+            constexpr int C8 = C::KC / 8;
+            constexpr int UNITS = C::WIN_POS * C8;
+            constexpr int BATCH = 4;
+            constexpr int NBATCH = (UNITS + C::PRODUCERS * BATCH - 1) / (C::PRODUCERS * BATCH);
+            struct Cursor {
+                int item, cc, b;
+            };
+            auto advance = [&](Cursor &c) {
+                if (++c.b == NBATCH) {
+                    c.b = 0;
+                    if (++c.cc == C::NCHUNK) {
+                        c.cc = 0;
+                        ++c.item;
+                    }
+                }
+            };
+            // geometry of unit u of the stage (item, cc): window position, channel group, source pointer (or null)
+            auto geom = [&](int n, int y0, int x0, int cc, int u, int &pos, int &c8, int &s) -> const float * {
+                pos = u / C8;
+                c8 = u - pos * C8;
+                const int wy = pos / C::PITCH, wx = pos - wy * C::PITCH;
+                int nn, y, x;
+                if (C::NI == 1) {
+                    s = 0;
+                    nn = n;
+                    y = y0 - 1 + wy;
+                    x = x0 - 1 + wx;
+                } else {
+                    s = wx / 10;
+                    nn = n + s;
+                    y = wy - 1;
+                    x = wx - s * 10 - 1;
+                }
+                if (u >= UNITS || y < 0 || y >= W || x < 0 || x >= W || nn >= p.nimg) return nullptr;
+                return (const float *)p.src + ((((long long)nn * W + y) * W + x) * CIN + cc * C::KC + c8 * 8);
+            };
+            auto issue = [&](const Cursor &c, float4 (&buf)[BATCH][2]) {
+                int n, y0, x0;
+                decode(c.item, n, y0, x0);
+#pragma unroll
+                for (int i = 0; i < BATCH; ++i) {
+                    int pos, c8, s;
+                    const float *src = geom(n, y0, x0, c.cc, ptid + C::PRODUCERS * (c.b * BATCH + i), pos, c8, s);
+                    if (src) {
+                        buf[i][0] = __ldg((const float4 *)src);
+                        buf[i][1] = __ldg((const float4 *)src + 1);
+                    }
+                }
+            };
+            auto consume = [&](const Cursor &c, float4 (&buf)[BATCH][2], uint32_t stage_u32) {
+                int n, y0, x0;
+                decode(c.item, n, y0, x0);
+#pragma unroll
+                for (int i = 0; i < BATCH; ++i) {
+                    const int u = ptid + C::PRODUCERS * (c.b * BATCH + i);
+                    int pos, c8, s;
+                    const float *src = geom(n, y0, x0, c.cc, u, pos, c8, s);
+                    if (u >= UNITS) continue;
+                    uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+                    if (src) {
+                        const float xv[8] = {buf[i][0].x, buf[i][0].y, buf[i][0].z, buf[i][0].w,
+                                             buf[i][1].x, buf[i][1].y, buf[i][1].z, buf[i][1].w};
+                        norm_split8(xv, tab_u32 + (s * CIN + c.cc * C::KC + c8 * 8) * 8, hi, lo);
+                    }
+                    store_chunk<C>(stage_u32, pos, c8, hi, lo);
+                }
+            };
+            float4 buf0[BATCH][2], buf1[BATCH][2];
+            Cursor cur = {item_begin, 0, 0}, nxt = cur;
+            if (cur.item < item_end) issue(nxt, buf0);
+            advance(nxt);
+            uint32_t stage_u32 = smem_base_u32;
+            auto step = [&](float4 (&bc)[BATCH][2], float4 (&bn)[BATCH][2]) {
+                if (nxt.item < item_end) issue(nxt, bn);
+                if (cur.b == 0) {
+                    if (cur.cc == 0) {
+                        int n, y0, x0;
+                        decode(cur.item, n, y0, x0);
+                        update_table(n);
+                    }
+                    const int sa = ait % C::A_STAGES;
+                    mbar_wait_bounded(&a_empty[sa], ((ait / C::A_STAGES) & 1u) ^ 1u);
+                    stage_u32 = smem_base_u32 + sa * C::A_STAGE;
+                }
+                if (!(p.dbg & 1)) consume(cur, bc, stage_u32);
+                if (cur.b == NBATCH - 1) {
+                    fence_proxy_async();
+                    mbar_arrive(&a_full[ait % C::A_STAGES]);
+                    ++ait;
+                }
+                advance(cur);
+                advance(nxt);
+            };
+            while (cur.item < item_end) {
+                step(buf0, buf1);
+                if (cur.item >= item_end) break;
+                step(buf1, buf0);
             }
         }
     }
