@@ -32,7 +32,7 @@ struct ebsd_encoder {
     int use_mma;                 // EBSD_ENCODER_PATH: 3 = fused producer/tcgen05/epilogue blocks (default, "fused"),
                                  // 2 = tcgen05 shifted-window path with finisher kernels ("mma"), 1 = first-generation
                                  // tcgen05 path ("mma1"), 0 = fp32 CUDA-core path ("simt")
-    int chunk;                   // images per pass of the fused path (EBSD_ENCODER_CHUNK)
+    int chunk, sub;              // images per pass / per early sub-chunk of the fused path (EBSD_ENCODER_CHUNK, _SUB)
     float *w_simt[EBSD_N_CONV];  // [tap][ci][co] fp32
     __half *w_mma[EBSD_N_CONV];  // tensor-path packing (encoder_mma.cuh), layers 1..9
     CUtensorMap w_map[EBSD_N_CONV];
@@ -407,17 +407,26 @@ int forward_chunk_mma2(const ebsd_encoder *enc, const void *pin, int dtype, int 
 
 
 // ------------------------------------------------------------------ third-generation path (encoder_fused.cuh)
-constexpr int kChunkFused = 296;                       // default images per pass (2 per SM: every late layer fills the GPU)
-constexpr size_t kFusedBuf0Floats = 64ull * 64 * 32;   // per image: pooled output of conv1 (largest tenant of buffer 0)
-constexpr size_t kFusedBuf1Floats = 64ull * 64 * 64;   // per image: output of conv2 (largest tenant of buffer 1)
+// Two-level chunking.  Blocks 0..3 (128x128 and 64x64 planes, 1.75 MB of raw fp32 per image) run over SUB-chunks
+// small enough that a block's output is still in the 126 MB L2 when the next block reads it and is overwritten by
+// the next sub-chunk before it is ever written back; blocks 4..9 (<= 0.5 MB per image) run over the whole chunk so
+// that even the 8x8 blocks fill all SMs.
+constexpr int kChunkFused = 296;                       // images per pass (2 per SM)
+constexpr int kSubFused = 74;                          // images per early sub-chunk (blocks 0..3)
+constexpr size_t kFusedRaw1Floats = 64ull * 64 * 32;   // per image: pooled output of conv1
+constexpr size_t kFusedRaw2Floats = 64ull * 64 * 64;   // per image: output of conv2
+constexpr size_t kFusedRaw3Floats = 32ull * 32 * 64;   // per image: pooled output of conv3 (largest tenant of late buffer 0)
+constexpr size_t kFusedRaw4Floats = 32ull * 32 * 128;  // per image: output of conv4 (largest tenant of late buffer 1)
 
 struct FusedWorkspace {
-    float *buf0, *buf1;
-    double *sums;  // [EBSD_N_CONV][chunk][128][2]
+    float *raw1, *raw2;    // sub-chunk level
+    float *late0, *late1;  // chunk level: conv3/5/7/9 outputs, conv4/6/8 outputs
+    double *sums;          // [EBSD_N_CONV][chunk][128][2]
     size_t bytes;
 };
 
-FusedWorkspace carve_fused(void *workspace, size_t chunk) {
+FusedWorkspace carve_fused(void *workspace, size_t chunk, size_t sub) {
+    if (sub > chunk) sub = chunk;
     uint8_t *p = (uint8_t *)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
     auto take = [&](size_t bytes) {
         uint8_t *r = p;
@@ -425,38 +434,64 @@ FusedWorkspace carve_fused(void *workspace, size_t chunk) {
         return r;
     };
     FusedWorkspace w;
-    w.buf0 = (float *)take(chunk * kFusedBuf0Floats * sizeof(float));
-    w.buf1 = (float *)take(chunk * kFusedBuf1Floats * sizeof(float));
+    w.raw1 = (float *)take(sub * kFusedRaw1Floats * sizeof(float));
+    w.raw2 = (float *)take(sub * kFusedRaw2Floats * sizeof(float));
+    w.late0 = (float *)take(chunk * kFusedRaw3Floats * sizeof(float));
+    w.late1 = (float *)take(chunk * kFusedRaw4Floats * sizeof(float));
     w.sums = (double *)take((size_t)EBSD_N_CONV * chunk * kSumsDoubles * sizeof(double));
     w.bytes = (size_t)(p - (uint8_t *)workspace);
     return w;
 }
 
-template <int CIN, int COUT, int W, int SRC>
+// fp32 [nimg,Wo,Wo,COUT] output as a 4-D tensor (c, x, y, n); box = (32 channels, bx, by, bn), 128B-swizzled in smem
+int make_out_map(CUtensorMap *map, const float *base, int cout, int wo, int nimg, int bx, int by, int bn) {
+    tensormap_encode_fn encode = get_tensormap_encode();
+    if (!encode) {
+        set_error("encoder: cuTensorMapEncodeTiled entry point not available");
+        return EBSD_ERR_CUDA;
+    }
+    const cuuint64_t gdim[4] = {(cuuint64_t)cout, (cuuint64_t)wo, (cuuint64_t)wo, (cuuint64_t)nimg};
+    const cuuint64_t gstride[3] = {(cuuint64_t)cout * 4, (cuuint64_t)wo * cout * 4, (cuuint64_t)wo * wo * cout * 4};
+    const cuuint32_t box[4] = {32u, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bn};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("encoder: cuTensorMapEncodeTiled(raw output) failed with %d", (int)cr);
+        return EBSD_ERR_CUDA;
+    }
+    return EBSD_OK;
+}
+
+template <int CIN, int COUT, int W, int SRC, bool POOL>
 int launch_fused(const ebsd_encoder *enc, int layer, const void *src, const double *src_sums, int src_plane,
-                 float *raw, double *sums, int nimg, bool pool, cudaStream_t st) {
-    using C = FusedCfg<CIN, COUT, W, SRC>;
+                 float *raw, double *sums, int nimg, cudaStream_t st) {
+    using C = FusedCfg<CIN, COUT, W, SRC, POOL>;
     static bool configured = false;
     if (!configured) {
-        EBSD_CUDA_TRY(cudaFuncSetAttribute(conv3x3_fused_kernel<CIN, COUT, W, SRC>,
+        EBSD_CUDA_TRY(cudaFuncSetAttribute(conv3x3_fused_kernel<CIN, COUT, W, SRC, POOL>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
+    CUtensorMap map_out;
+    int rc;
+    if (C::NI == 1) rc = make_out_map(&map_out, raw, COUT, POOL ? W / 2 : W, nimg, POOL ? 4 : 8, POOL ? 2 : 4, 1);
+    else rc = make_out_map(&map_out, raw, COUT, POOL ? W / 2 : W, nimg, POOL ? 4 : 8, POOL ? 1 : 2, 2);
+    if (rc) return rc;
     FusedParams p;
     p.src = src;
     p.src_sums = src_sums;
     p.inv_src_plane = 1.0 / (double)src_plane;
     p.w0 = enc->w_simt[0];
-    p.raw = raw;
     p.sums = sums;
     p.nimg = nimg;
     p.nitems = C::NI == 1 ? nimg * C::ITEMS_PER_IMAGE : (nimg + C::NI - 1) / C::NI;
-    p.pool = pool ? 1 : 0;
     p.dbg = g_debug_flags;
     const int sms = sm_count();
     const int per = (p.nitems + sms - 1) / sms;
     const int grid = (p.nitems + per - 1) / per;
-    conv3x3_fused_kernel<CIN, COUT, W, SRC><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(enc->w_map[layer], p);
+    conv3x3_fused_kernel<CIN, COUT, W, SRC, POOL><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(enc->w_map[layer], map_out, p);
     EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }
@@ -464,20 +499,19 @@ int launch_fused(const ebsd_encoder *enc, int layer, const void *src, const doub
 // src: layer 1 -> patterns (dtype), layers 2..9 -> raw output of layer-1 ... ; sums must be zeroed by the caller
 int fused_dispatch(const ebsd_encoder *enc, int layer, int dtype, const void *src, const double *src_sums,
                    int src_plane, float *raw, double *sums, int nimg, cudaStream_t st) {
-    const bool pool = kPlan[layer].pool;
     switch (layer) {
         case 1:
             if (dtype == EBSD_PATTERN_U8)
-                return launch_fused<32, 32, 128, SRC_U8>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
-            return launch_fused<32, 32, 128, SRC_F32>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
-        case 2: return launch_fused<32, 64, 64, SRC_RAW>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
-        case 3: return launch_fused<64, 64, 64, SRC_RAW>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
-        case 4: return launch_fused<64, 128, 32, SRC_RAW>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
-        case 5: return launch_fused<128, 128, 32, SRC_RAW>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
-        case 6:
-        case 7: return launch_fused<128, 128, 16, SRC_RAW>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
-        case 8:
-        case 9: return launch_fused<128, 128, 8, SRC_RAW>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, pool, st);
+                return launch_fused<32, 32, 128, SRC_U8, true>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, st);
+            return launch_fused<32, 32, 128, SRC_F32, true>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, st);
+        case 2: return launch_fused<32, 64, 64, SRC_RAW, false>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, st);
+        case 3: return launch_fused<64, 64, 64, SRC_RAW, true>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, st);
+        case 4: return launch_fused<64, 128, 32, SRC_RAW, false>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, st);
+        case 5: return launch_fused<128, 128, 32, SRC_RAW, true>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, st);
+        case 6: return launch_fused<128, 128, 16, SRC_RAW, false>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, st);
+        case 7: return launch_fused<128, 128, 16, SRC_RAW, true>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, st);
+        case 8: return launch_fused<128, 128, 8, SRC_RAW, false>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, st);
+        case 9: return launch_fused<128, 128, 8, SRC_RAW, true>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, st);
     }
     set_error("encoder: no fused kernel for layer %d", layer);
     return EBSD_ERR_ARG;
@@ -490,24 +524,35 @@ int conv0_stats(const ebsd_encoder *enc, const void *pats, int dtype, int nimg, 
     return EBSD_OK;
 }
 
-// One chunk of the fused path: 12 launches (statistics of conv0, nine fused blocks, heads) + one memset.
-int forward_chunk_fused(const ebsd_encoder *enc, const void *pin, int dtype, int nimg, size_t chunk, float *mu,
-                        float *logvar, const FusedWorkspace &w, cudaStream_t st) {
+// One chunk of the fused path: per sub-chunk conv0 statistics + blocks 1..3, then blocks 4..9 and the heads.
+int forward_chunk_fused(const ebsd_encoder *enc, const void *pin, int dtype, int nimg, size_t chunk, size_t sub,
+                        float *mu, float *logvar, const FusedWorkspace &w, cudaStream_t st) {
     int rc;
     const size_t lstride = chunk * kSumsDoubles;  // doubles per layer in w.sums
+    const size_t px_bytes = dtype == EBSD_PATTERN_U8 ? 1 : 4;
+    auto layer_sums = [&](int l, int n0) { return w.sums + (size_t)l * lstride + (size_t)n0 * kPlan[l].cout * 2; };
+    auto plane = [&](int l) { return kPlan[l].hw * kPlan[l].hw; };
     EBSD_CUDA_TRY(cudaMemsetAsync(w.sums, 0, (size_t)EBSD_N_CONV * lstride * sizeof(double), st));
-    if ((rc = conv0_stats(enc, pin, dtype, nimg, w.sums, st))) return rc;
-    const void *src = pin;
-    for (int l = 1; l < EBSD_N_CONV; ++l) {
-        float *dst = (l & 1) ? w.buf0 : w.buf1;
-        const int src_plane = kPlan[l - 1].hw * kPlan[l - 1].hw;
-        if ((rc = fused_dispatch(enc, l, dtype, src, w.sums + (size_t)(l - 1) * lstride, src_plane, dst,
-                                 w.sums + (size_t)l * lstride, nimg, st)))
+    for (int s0 = 0; s0 < nimg; s0 += (int)sub) {
+        const int ns = nimg - s0 < (int)sub ? nimg - s0 : (int)sub;
+        const void *pats = (const uint8_t *)pin + (size_t)s0 * 128 * 128 * px_bytes;
+        if ((rc = conv0_stats(enc, pats, dtype, ns, layer_sums(0, s0), st))) return rc;
+        if ((rc = fused_dispatch(enc, 1, dtype, pats, layer_sums(0, s0), plane(0), w.raw1, layer_sums(1, s0), ns, st)))
+            return rc;
+        if ((rc = fused_dispatch(enc, 2, dtype, w.raw1, layer_sums(1, s0), plane(1), w.raw2, layer_sums(2, s0), ns, st)))
+            return rc;
+        if ((rc = fused_dispatch(enc, 3, dtype, w.raw2, layer_sums(2, s0), plane(2), w.late0 + (size_t)s0 * kFusedRaw3Floats,
+                                 layer_sums(3, s0), ns, st)))
+            return rc;
+    }
+    const float *src = w.late0;
+    for (int l = 4; l < EBSD_N_CONV; ++l) {
+        float *dst = (l & 1) ? w.late0 : w.late1;
+        if ((rc = fused_dispatch(enc, l, dtype, src, layer_sums(l - 1, 0), plane(l - 1), dst, layer_sums(l, 0), nimg, st)))
             return rc;
         src = dst;
     }
-    heads_norm_kernel<<<nimg, 256, 0, st>>>((const float *)src, w.sums + (size_t)(EBSD_N_CONV - 1) * lstride, enc->wh,
-                                           enc->bh, mu, logvar);
+    heads_norm_kernel<<<nimg, 256, 0, st>>>(src, layer_sums(EBSD_N_CONV - 1, 0), enc->wh, enc->bh, mu, logvar);
     EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }
@@ -566,9 +611,14 @@ int ebsd_encoder_create(ebsd_encoder **out, const ebsd_weights *w, int device, v
     if (path && strcmp(path, "mma1") == 0) enc->use_mma = 1;
     if (path && strcmp(path, "mma") == 0) enc->use_mma = 2;
     enc->chunk = kChunkFused;
+    enc->sub = kSubFused;
     if (const char *c = getenv("EBSD_ENCODER_CHUNK")) {
         const int v = atoi(c);
         if (v >= 1 && v <= 4096) enc->chunk = v;
+    }
+    if (const char *c = getenv("EBSD_ENCODER_SUB")) {
+        const int v = atoi(c);
+        if (v >= 1 && v <= 4096) enc->sub = v;
     }
     for (int i = 1; i < EBSD_N_CONV; ++i) {
         const int cin = kPlan[i].cin, cout = kPlan[i].cout, kc = cin < 64 ? cin : 64;
@@ -603,7 +653,7 @@ size_t ebsd_encoder_workspace_bytes(const ebsd_encoder *enc, int64_t B) {
     const size_t nimg = (size_t)(B < chunk_cap ? B : chunk_cap);
     if (enc && enc->use_mma == 3) {
         const size_t c = (size_t)(B < enc->chunk ? B : enc->chunk);
-        return carve_fused(nullptr, c).bytes + 1024;
+        return carve_fused(nullptr, c, (size_t)enc->sub).bytes + 1024;
     }
     if (enc && enc->use_mma == 2) return carve_mma2(nullptr, nimg).bytes + 1024;
     // raw fp32 + (fp32 activations | fp16 hi + fp16 lo planes) + plane sums
@@ -635,11 +685,11 @@ int ebsd_encoder_forward(ebsd_encoder *enc, const void *patterns, int dtype, int
     const size_t px_bytes = dtype == EBSD_PATTERN_U8 ? 1 : 4;
     if (enc->use_mma == 3) {
         const size_t fchunk = (size_t)(B < enc->chunk ? B : enc->chunk);
-        const FusedWorkspace wf = carve_fused(workspace, fchunk);
+        const FusedWorkspace wf = carve_fused(workspace, fchunk, (size_t)enc->sub);
         for (int64_t b0 = 0; b0 < B; b0 += (int64_t)fchunk) {
             const int nimg = (int)((B - b0) < (int64_t)fchunk ? (B - b0) : (int64_t)fchunk);
             const void *pin = (const uint8_t *)patterns + (size_t)b0 * 128 * 128 * px_bytes;
-            if ((rc = forward_chunk_fused(enc, pin, dtype, nimg, fchunk, mu + b0 * 16,
+            if ((rc = forward_chunk_fused(enc, pin, dtype, nimg, fchunk, (size_t)enc->sub, mu + b0 * 16,
                                           logvar ? logvar + b0 * 16 : nullptr, wf, st)))
                 return rc;
         }

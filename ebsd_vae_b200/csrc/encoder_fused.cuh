@@ -29,9 +29,10 @@ namespace ebsd {
 
 enum FusedSrc { SRC_U8 = 0, SRC_F32 = 1, SRC_RAW = 2 };
 
-template <int CIN_, int COUT_, int W_, int SRC_>
+template <int CIN_, int COUT_, int W_, int SRC_, bool POOL_>
 struct FusedCfg {
     static constexpr int CIN = CIN_, COUT = COUT_, W = W_, SRC = SRC_;
+    static constexpr bool POOL = POOL_;                      // 2x2 max-pool of the raw output in the epilogue
     static constexpr bool FIRST = SRC_ != SRC_RAW;           // conv0 is computed by the producers (CIN = 32, W = 128)
     static constexpr int NI = W == 8 ? 2 : 1;                // images interleaved in one window row
     static constexpr int NT = W >= 128 ? 4 : (W >= 64 ? 2 : 1);  // tiles per work item
@@ -50,7 +51,11 @@ struct FusedCfg {
     static constexpr int B_TILE = 2 * COUT * ROWB;           // [w_hi; w_lo] of one (tap, K chunk)
     static constexpr bool RESIDENT_B = 9 * NCHUNK * B_TILE <= 80 * 1024;
     static constexpr int A_STAGES = 2;
-    static constexpr int EXTRA = 8192;                       // barriers, tables, conv0 patch
+    // output staging for the TMA stores: per epilogue warp one [32 or 8 rows][128 B] box, 128B-swizzled
+    static constexpr int WSTG = POOL ? 1024 : 4096;
+    static constexpr int NSB = (!POOL && RESIDENT_B) ? 2 : 1; // staging buffers per warp
+    static constexpr int STAGING = 4 * NSB * WSTG;
+    static constexpr int EXTRA = 8192 + STAGING;             // barriers, tables, conv0 patch | staging
     static constexpr int B_FIT = (226 * 1024 - 1024 - EXTRA - A_STAGES * A_STAGE) / B_TILE;
     static constexpr int B_STAGES = RESIDENT_B ? 9 * NCHUNK : (B_FIT > 6 ? 6 : B_FIT);
     static constexpr int B_BYTES = B_STAGES * B_TILE;
@@ -73,11 +78,9 @@ struct FusedParams {
     const double *src_sums;  // [nimg,CIN,2] plane sums (sum, sum of squares) of the block that produced src
     double inv_src_plane;    // 1 / number of pixels those sums run over
     const float *w0;         // FIRST: conv0 weights [tap][32] fp32
-    float *raw;              // out: fp32 [nimg,Wo,Wo,COUT], Wo = W/2 when pooling
     double *sums;            // out: [nimg,COUT,2], must be zero on entry
     int nimg;
     int nitems;
-    int pool;
     int dbg;                 // profiling switches (ebsd_debug_set_flags): 1 producers write nothing, 2 no MMAs,
                              // 4 epilogue does nothing but release TMEM, 8 no plane statistics, 16 no stores
 };
@@ -88,6 +91,18 @@ __device__ __forceinline__ uint64_t umma_smem_desc_g(uint32_t saddr) {
     constexpr uint64_t sbo = ((uint64_t)GROUP_ROWS * ROWB) >> 4;
     return (uint64_t)((saddr & 0x3ffffu) >> 4) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -142,10 +157,12 @@ __device__ __forceinline__ void store_chunk(uint32_t stage_u32, int pos, int c8,
     sts128(a_lo ^ (((a_lo >> 7) & C::SWMASK) << 4), lo);
 }
 
-template <int CIN, int COUT, int W, int SRC>
+// map_out: fp32 [nimg,Wo,Wo,COUT] raw output (Wo = W/2 when pooling), box = one epilogue warp's share of a tile
+template <int CIN, int COUT, int W, int SRC, bool POOL>
 __global__ void __launch_bounds__(512, 1)
-conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParams p) {
-    using C = FusedCfg<CIN, COUT, W, SRC>;
+conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
+                     const FusedParams p) {
+    using C = FusedCfg<CIN, COUT, W, SRC, POOL>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *smem_b = smem + C::A_STAGES * C::A_STAGE;
@@ -179,6 +196,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
         }
         mbar_fence_init();
         tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_out);
     }
     if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
     tc_fence_before();
@@ -307,6 +325,11 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
         const int b_par = C::NI == 1 ? (g & 1) : ((g >> 1) & 1);
         const int im = C::NI == 1 ? 0 : (g & 1);  // image slot of this lane (NI == 2)
         const int yl = C::NI == 1 ? g : (g >> 1); // image row of this lane relative to the tile
+        // staging rows of this lane: pooled pixel / un-pooled pixel in the warp's TMA box ([n][y][x] order)
+        const int prow = C::NI == 1 ? ((lane >> 4) * 4 + (xl >> 1)) : (im * 4 + (xl >> 1));
+        const int urow = C::NI == 1 ? lane : (im * 16 + ((lane >> 4) & 1) * 8 + xl);
+        const uint32_t stg_u32 = smem_u32(extra + 8192) + (uint32_t)(quarter * C::NSB * C::WSTG);
+        int sbuf = 0;
         float acc1[NCB][C::NI], acc2[NCB][C::NI];
 #pragma unroll
         for (int cb = 0; cb < NCB; ++cb)
@@ -357,7 +380,6 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * C::ACC_COLS);
 #pragma unroll 1
             for (int t = 0; t < ((p.dbg & 4) ? 0 : C::NT); ++t) {
-                const int y = y0 + yl, x = x0 + 8 * t + xl;
 #pragma unroll
                 for (int cb = 0; cb < NCB; ++cb) {
                     float v[32], w[32];
@@ -366,7 +388,11 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] + w[i] : 0.f;
-                    if (p.pool) {
+                    // ---- store through shared memory: one TMA box per warp, block of 32 channels and tile
+                    const uint32_t stg = stg_u32 + (uint32_t)(sbuf * C::WSTG);
+                    if (lane == 0) bulk_wait_read<C::NSB - 1>();
+                    __syncwarp();
+                    if (POOL) {
                         // transposing butterfly: after the x-pair step a lane keeps 16 channels, after the row-pair
                         // step 8 channels, each the maximum over the 2x2 block
                         float r[16], o[8];
@@ -382,18 +408,35 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
                             const float keep = b_par ? r[8 + i] : r[i];
                             o[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, PV));
                         }
-                        if (valid && !(p.dbg & 16)) {
-                            float *out = p.raw + ((((long long)(n + im) * (W / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * COUT +
-                                                  cb * 32 + a_par * 16 + b_par * 8);
-                            *(float4 *)out = make_float4(o[0], o[1], o[2], o[3]);
-                            *(float4 *)(out + 4) = make_float4(o[4], o[5], o[6], o[7]);
-                        }
-                    } else if (valid && !(p.dbg & 16)) {
-                        float *out = p.raw + ((((long long)(n + im) * W + y) * W + x) * COUT + cb * 32);
+                        const int ch = a_par * 4 + b_par * 2;  // first 16-byte chunk of this lane's 8 channels
+                        const uint32_t rowa = stg + (uint32_t)(prow * 128);
+                        sts128(rowa + (uint32_t)(((ch) ^ (prow & 7)) << 4),
+                               make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])));
+                        sts128(rowa + (uint32_t)(((ch + 1) ^ (prow & 7)) << 4),
+                               make_uint4(__float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7])));
+                    } else {
+                        const uint32_t rowa = stg + (uint32_t)(urow * 128);
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            *(float4 *)(out + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        for (int i = 0; i < 8; ++i)
+                            sts128(rowa + (uint32_t)((i ^ (urow & 7)) << 4),
+                                   make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
+                                              __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3])));
                     }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && !(p.dbg & 16)) {
+                        int cx, cy;
+                        if (C::NI == 1) {
+                            cx = POOL ? (x0 + 8 * t) >> 1 : x0 + 8 * t;
+                            cy = POOL ? (y0 + 4 * quarter) >> 1 : y0 + 4 * quarter;
+                        } else {
+                            cx = 0;
+                            cy = POOL ? quarter : 2 * quarter;
+                        }
+                        tma_store_4d(&map_out, stg, cb * 32, cx, cy, n);
+                        bulk_commit();
+                    }
+                    sbuf = (sbuf + 1) % C::NSB;
                     // plane statistics of the un-pooled output
                     if (p.dbg & 8) continue;
                     if (C::NI == 1) {
@@ -421,6 +464,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const FusedParam
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
         }
         flush();
+        if (lane == 0) bulk_wait_all();  // the staging buffers must outlive the TMA reads; stores complete before exit
     } else if (warp >= 8) {
         // ===================== producers: build the fp16 hi / lo window in shared memory
         const int ptid = threadIdx.x - 256;
