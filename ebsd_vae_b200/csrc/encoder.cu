@@ -411,8 +411,9 @@ int forward_chunk_mma2(const ebsd_encoder *enc, const void *pin, int dtype, int 
 // small enough that a block's output is still in the 126 MB L2 when the next block reads it and is overwritten by
 // the next sub-chunk before it is ever written back; blocks 4..9 (<= 0.5 MB per image) run over the whole chunk so
 // that even the 8x8 blocks fill all SMs.
-constexpr int kChunkFused = 296;                       // images per pass (2 per SM)
-constexpr int kSubFused = 74;                          // images per early sub-chunk (blocks 0..3)
+constexpr int kChunkFused = 1184;                      // images per pass (8 per SM): long launches amortise pipeline fill
+constexpr int kSubFused = 1184;                        // images per early sub-chunk (blocks 0..3); measured: L2 residency
+                                                       // gains less than the extra launches cost, so sub = chunk
 constexpr size_t kFusedRaw1Floats = 64ull * 64 * 32;   // per image: pooled output of conv1
 constexpr size_t kFusedRaw2Floats = 64ull * 64 * 64;   // per image: output of conv2
 constexpr size_t kFusedRaw3Floats = 32ull * 32 * 64;   // per image: pooled output of conv3 (largest tenant of late buffer 0)
@@ -518,7 +519,10 @@ int fused_dispatch(const ebsd_encoder *enc, int layer, int dtype, const void *sr
 }
 
 int conv0_stats(const ebsd_encoder *enc, const void *pats, int dtype, int nimg, double *sums0, cudaStream_t st) {
-    if (dtype == EBSD_PATTERN_U8) conv0_stats_kernel<true><<<dim3(16, nimg), 256, 0, st>>>(pats, enc->w_simt[0], sums0);
+    // uint8: exact integer autocorrelation (patterns must be 4-byte aligned); float32: conv0 recomputed on CUDA cores
+    if (dtype == EBSD_PATTERN_U8 && ((uintptr_t)pats & 3) == 0)
+        conv0_stats_u8_kernel<<<nimg, 256, 0, st>>>((const uint8_t *)pats, enc->w_simt[0], sums0);
+    else if (dtype == EBSD_PATTERN_U8) conv0_stats_kernel<true><<<dim3(16, nimg), 256, 0, st>>>(pats, enc->w_simt[0], sums0);
     else conv0_stats_kernel<false><<<dim3(16, nimg), 256, 0, st>>>(pats, enc->w_simt[0], sums0);
     EBSD_LAUNCH_CHECK();
     return EBSD_OK;

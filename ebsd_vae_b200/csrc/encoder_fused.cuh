@@ -698,6 +698,82 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// Plane statistics of conv0's output WITHOUT running conv0 (uint8 patterns).  conv0 has one input channel, so for
+// output channel c:   sum_p o_c(p)   = sum_t w[t][c] S[t] / 255,        S[t]    = sum_p k(p + t)
+//                     sum_p o_c(p)^2 = sum_{t,t'} w[t][c] w[t'][c] R[t][t'] / 255^2,  R[t][t'] = sum_p k(p + t) k(p + t')
+// with k the uint8 pixel (zero outside the image) and t, t' the nine taps.  S and R are exact integers: each lane
+// holds four horizontally adjacent pixels per tap as one packed word and a DP4A accumulates four products.
+// One CTA per image, 8 warps x 16 rows; writes sums0[n][32][2] (no atomics).
+__global__ void __launch_bounds__(256) conv0_stats_u8_kernel(const uint8_t *__restrict__ pats, const float *__restrict__ w0,
+                                                             double *__restrict__ sums0) {
+    __shared__ unsigned red[8][54];
+    __shared__ unsigned tot[54];
+    const long long n = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned *img = (const unsigned *)(pats + n * 16384);
+    auto load_row = [&](int y, unsigned &wm, unsigned &wc, unsigned &wp) {
+        unsigned w = 0u;
+        if (y >= 0 && y < 128) w = __ldg(img + y * 32 + lane);
+        unsigned prev = __shfl_up_sync(0xffffffffu, w, 1), next = __shfl_down_sync(0xffffffffu, w, 1);
+        if (lane == 0) prev = 0u;
+        if (lane == 31) next = 0u;
+        wm = __funnelshift_l(prev, w, 8);   // pixels x-1 .. x+2
+        wc = w;                             // pixels x   .. x+3
+        wp = __funnelshift_r(w, next, 8);   // pixels x+1 .. x+4
+    };
+    unsigned acc[54];
+#pragma unroll
+    for (int i = 0; i < 54; ++i) acc[i] = 0u;
+    unsigned t[9];
+    const int y0 = warp * 16;
+    load_row(y0 - 1, t[0], t[1], t[2]);
+    load_row(y0, t[3], t[4], t[5]);
+#pragma unroll 1
+    for (int y = y0; y < y0 + 16; ++y) {
+        load_row(y + 1, t[6], t[7], t[8]);
+        int k = 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            acc[i] = __dp4a(t[i], 0x01010101u, acc[i]);
+#pragma unroll
+            for (int j = i; j < 9; ++j, ++k) acc[k] = __dp4a(t[i], t[j], acc[k]);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) t[i] = t[i + 3];
+    }
+#pragma unroll
+    for (int i = 0; i < 54; ++i) {
+        unsigned v = acc[i];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 54) {
+        unsigned v = 0u;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        tot[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int c = threadIdx.x;
+        double wt[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) wt[i] = (double)w0[i * 32 + c];
+        double s1 = 0.0, s2 = 0.0;
+        int k = 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            s1 += wt[i] * (double)tot[i];
+#pragma unroll
+            for (int j = i; j < 9; ++j, ++k) s2 += (i == j ? 1.0 : 2.0) * wt[i] * wt[j] * (double)tot[k];
+        }
+        sums0[(n * 32 + c) * 2 + 0] = s1 / 255.0;
+        sums0[(n * 32 + c) * 2 + 1] = s2 / 65025.0;
+    }
+}
+
 // mu / logvar heads (latice/model.py:57-58, 127-129) straight from the last block's pooled raw output
 // raw9 [n,4,4,128] + its plane sums (64 pixels): InstanceNorm + LeakyReLU here, then the two 2048 -> 16 products.
 __global__ void __launch_bounds__(256) heads_norm_kernel(const float *__restrict__ raw9, const double *__restrict__ sums9,
