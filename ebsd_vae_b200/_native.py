@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libebsd_b200.so")
+# EBSD_B200_LIB selects another build of the same library (A/B timing of compile-time variants); no fallback either way
+LIB_PATH = os.environ.get("EBSD_B200_LIB") or os.path.join(_HERE, "libebsd_b200.so")
 
 OK = 0
 PATTERN_U8 = 0

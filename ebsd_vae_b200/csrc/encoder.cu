@@ -36,6 +36,7 @@ struct ebsd_encoder {
     float *w_simt[EBSD_N_CONV];  // [tap][ci][co] fp32
     __half *w_mma[EBSD_N_CONV];  // tensor-path packing (encoder_mma.cuh), layers 1..9
     CUtensorMap w_map[EBSD_N_CONV];
+    CUtensorMap w_map_fused[EBSD_N_CONV];  // box = the slice one CTA of a cluster fetches (encoder_fused.cuh)
     float *wh;                   // [32][2048] permuted heads
     float *bh;                   // [32]
 };
@@ -132,7 +133,7 @@ int make_act_map(CUtensorMap *map, const __half *base, int cin, int hw, int nimg
     return EBSD_OK;
 }
 
-int make_weight_map(CUtensorMap *map, const __half *base, int cin, int cout, int kc) {
+int make_weight_map(CUtensorMap *map, const __half *base, int cin, int cout, int kc, int box_rows = 0) {
     tensormap_encode_fn encode = get_tensormap_encode();
     if (!encode) {
         set_error("encoder: cuTensorMapEncodeTiled entry point not available");
@@ -141,7 +142,7 @@ int make_weight_map(CUtensorMap *map, const __half *base, int cin, int cout, int
     const int rows = 9 * (cin / kc) * 2 * cout;
     const cuuint64_t gdim[2] = {(cuuint64_t)kc, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)kc * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(2 * cout)};
+    const cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(box_rows > 0 ? box_rows : 2 * cout)};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)base, gdim, gstride, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -444,6 +445,14 @@ FusedWorkspace carve_fused(void *workspace, size_t chunk, size_t sub) {
     return w;
 }
 
+// rows of the packed weights one CTA fetches per (tap, K chunk): the whole [w_hi; w_lo] tile, or its 1/CL slice
+// when the block streams its weights through a cluster (FusedCfg::RESIDENT_B / CL)
+int fused_weight_box_rows(int layer) {
+    const int cin = kPlan[layer].cin, cout = kPlan[layer].cout, kc = cin < 64 ? cin : 64;
+    const bool resident = 9 * (cin / kc) * 2 * cout * kc * 2 <= 80 * 1024;
+    return resident ? 2 * cout : 2 * cout / EBSD_CL;
+}
+
 // fp32 [nimg,Wo,Wo,COUT] output as a 4-D tensor (c, x, y, n); box = (32 channels, bx, by, bn), 128B-swizzled in smem
 int make_out_map(CUtensorMap *map, const float *base, int cout, int wo, int nimg, int bx, int by, int bn) {
     tensormap_encode_fn encode = get_tensormap_encode();
@@ -489,10 +498,37 @@ int launch_fused(const ebsd_encoder *enc, int layer, const void *src, const doub
     p.nimg = nimg;
     p.nitems = C::NI == 1 ? nimg * C::ITEMS_PER_IMAGE : (nimg + C::NI - 1) / C::NI;
     p.dbg = g_debug_flags;
-    const int sms = sm_count();
-    const int per = (p.nitems + sms - 1) / sms;
-    const int grid = (p.nitems + per - 1) / per;
-    conv3x3_fused_kernel<CIN, COUT, W, SRC, POOL><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(enc->w_map[layer], map_out, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(C::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C::CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // persistent grid: as many CTAs as can be co-resident (clusters must fit inside a GPC), balanced over the items
+    static int max_ctas = 0;
+    if (max_ctas == 0) {
+        max_ctas = sm_count();
+        if (C::CL > 1) {
+            cfg.gridDim = dim3(max_ctas / C::CL * C::CL);
+            int nclusters = 0;
+            EBSD_CUDA_TRY(cudaOccupancyMaxActiveClusters(&nclusters, conv3x3_fused_kernel<CIN, COUT, W, SRC, POOL>, &cfg));
+            if (nclusters < 1) {
+                set_error("encoder: a cluster of %d CTAs of the fused block kernel does not fit on this device", C::CL);
+                return EBSD_ERR_CUDA;
+            }
+            if (nclusters * C::CL < max_ctas) max_ctas = nclusters * C::CL;
+        }
+    }
+    const int per = (p.nitems + max_ctas - 1) / max_ctas;
+    int grid = (p.nitems + per - 1) / per;
+    grid = (grid + C::CL - 1) / C::CL * C::CL;
+    cfg.gridDim = dim3(grid);
+    EBSD_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_fused_kernel<CIN, COUT, W, SRC, POOL>, enc->w_map_fused[layer], map_out, p));
     EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }
@@ -631,6 +667,7 @@ int ebsd_encoder_create(ebsd_encoder **out, const ebsd_weights *w, int device, v
         pack_conv_weights_mma_kernel<<<(total + 255) / 256, 256, 0, st>>>(w->conv_w[i], enc->w_mma[i], cin, cout, kc);
         EBSD_LAUNCH_CHECK();
         if ((rc = make_weight_map(&enc->w_map[i], enc->w_mma[i], cin, cout, kc))) return rc;
+        if ((rc = make_weight_map(&enc->w_map_fused[i], enc->w_mma[i], cin, cout, kc, fused_weight_box_rows(i)))) return rc;
     }
     EBSD_CUDA_TRY(cudaMalloc(&enc->wh, 32 * 2048 * sizeof(float)));
     EBSD_CUDA_TRY(cudaMalloc(&enc->bh, 32 * sizeof(float)));

@@ -29,6 +29,10 @@ namespace ebsd {
 
 enum FusedSrc { SRC_U8 = 0, SRC_F32 = 1, SRC_RAW = 2 };
 
+#ifndef EBSD_CL
+#define EBSD_CL 2   // cluster size of the blocks whose weights are streamed (1, 2 or 4)
+#endif
+
 template <int CIN_, int COUT_, int W_, int SRC_, bool POOL_>
 struct FusedCfg {
     static constexpr int CIN = CIN_, COUT = COUT_, W = W_, SRC = SRC_;
@@ -50,6 +54,11 @@ struct FusedCfg {
     static constexpr int A_STAGE = 2 * A_PLANE;              // hi + lo
     static constexpr int B_TILE = 2 * COUT * ROWB;           // [w_hi; w_lo] of one (tap, K chunk)
     static constexpr bool RESIDENT_B = 9 * NCHUNK * B_TILE <= 80 * 1024;
+    // Streamed weights: a cluster of CL CTAs shares every [w_hi; w_lo] tile -- each CTA fetches 1/CL of it and
+    // multicasts that slice into all CL shared memories, so the L2 -> SM weight traffic drops by CL.
+    static constexpr int CL = RESIDENT_B ? 1 : EBSD_CL;
+    static constexpr int B_SLICE_ROWS = 2 * COUT / CL;
+    static constexpr int B_SLICE = B_TILE / CL;
     static constexpr int A_STAGES = 2;
     // output staging for the TMA stores: per epilogue warp one [32 or 8 rows][128 B] box, 128B-swizzled
     static constexpr int WSTG = POOL ? 1024 : 4096;
@@ -104,6 +113,29 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap *map, int c0, int c1, uint32_t bar,
+                                               uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::
+            "r"(smem_dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -131,12 +163,15 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 }
 
 // y = leaky(x * scale + shift) split into fp16 hi / lo; eight values -> two 16-byte chunks.
-// tab_u32: shared address of eight (scale, shift) pairs.
-__device__ __forceinline__ void norm_split8(const float (&x)[8], uint32_t tab_u32, uint4 &hi, uint4 &lo) {
+// The (scale, shift) table is laid out [pair j = 0..3][8-channel group][2 channels] so that the eight lanes that
+// handle the eight channel groups of one position read 128 contiguous bytes (no bank conflicts): the pairs of
+// channels 2j, 2j+1 of group c8 sit at tab + j * jstride + c8 * 16.  tab_u32 already includes c8 * 16.
+__device__ __forceinline__ void norm_split8(const float (&x)[8], uint32_t tab_u32, uint32_t jstride, uint4 &hi,
+                                            uint4 &lo) {
     __half2 h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float4 tt = lds128(tab_u32 + j * 16);
+        const float4 tt = lds128(tab_u32 + j * jstride);
         const float2 t0 = make_float2(tt.x, tt.y), t1 = make_float2(tt.z, tt.w);
         float a = fmaf(x[2 * j], t0.x, t0.y), b = fmaf(x[2 * j + 1], t1.x, t1.y);
         a = fmaxf(a, 0.02f * a);
@@ -162,6 +197,7 @@ template <int CIN, int COUT, int W, int SRC, bool POOL>
 __global__ void __launch_bounds__(512, 1)
 conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
                      const FusedParams p) {
+    // map_w: box = [KC, 2*COUT / CL] rows of the packed weights (the whole tile when CL = 1)
     using C = FusedCfg<CIN, COUT, W, SRC, POOL>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -188,7 +224,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         }
         for (int s = 0; s < C::B_STAGES; ++s) {
             mbar_init(&b_full[s], 1);
-            mbar_init(&b_empty[s], 1);
+            mbar_init(&b_empty[s], C::CL);   // one tcgen05.commit from every CTA of the cluster
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull_bar[b], 1);
@@ -201,6 +237,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (C::CL > 1) cluster_sync_all();  // peers' barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -208,7 +245,10 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     // flushed once per image per warp instead of once per tile
     const int per_cta = (p.nitems + (int)gridDim.x - 1) / (int)gridDim.x;
     const int item_begin = (int)blockIdx.x * per_cta;
-    const int item_end = item_begin + per_cta < p.nitems ? item_begin + per_cta : p.nitems;
+    // CL > 1: every CTA of a cluster runs the same number of items (the weight ring advances in lock step); items
+    // beyond nitems decode to images >= nimg, which every role already treats as "nothing to load or store".
+    const int item_end = C::CL > 1 ? item_begin + per_cta
+                                   : (item_begin + per_cta < p.nitems ? item_begin + per_cta : p.nitems);
 
     if (warp == 0) {
         // ===================== weight loads (TMA)
@@ -226,8 +266,15 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                             const int sb = bit % C::B_STAGES;
                             mbar_wait_bounded(&b_empty[sb], ((bit / C::B_STAGES) & 1u) ^ 1u);
                             mbar_expect_tx(&b_full[sb], C::B_TILE);
-                            tma_load_2d(smem_b + sb * C::B_TILE, &map_w, 0, (tap * C::NCHUNK + cc) * 2 * COUT,
-                                        &b_full[sb]);
+                            if (C::CL == 1) {
+                                tma_load_2d(smem_b + sb * C::B_TILE, &map_w, 0, (tap * C::NCHUNK + cc) * 2 * COUT,
+                                            &b_full[sb]);
+                            } else {
+                                const int rank = (int)cluster_ctarank();
+                                tma_load_2d_mc(smem_u32(smem_b + sb * C::B_TILE + rank * C::B_SLICE), &map_w, 0,
+                                               (tap * C::NCHUNK + cc) * 2 * COUT + rank * C::B_SLICE_ROWS,
+                                               smem_u32(&b_full[sb]), (uint16_t)((1u << C::CL) - 1));
+                            }
                         }
             }
         }
@@ -306,7 +353,8 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                                     if (!(p.dbg & 2)) umma_f16(d_item + t * 2 * COUT,
                                              umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_lo + shift + t * 8 * C::ROWB + k * 32),
                                              umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_n1, 1u);
-                            umma_commit(&b_empty[sb]);
+                            if (C::CL == 1) umma_commit(&b_empty[sb]);
+                            else umma_commit_mc(&b_empty[sb], (uint16_t)((1u << C::CL) - 1));
                         }
                     }
                     umma_commit(&a_empty[sa]);
@@ -424,7 +472,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0 && !(p.dbg & 16)) {
+                    if (lane == 0 && n < p.nimg && !(p.dbg & 16)) {
                         int cx, cy;
                         if (C::NI == 1) {
                             cx = POOL ? (x0 + 8 * t) >> 1 : x0 + 8 * t;
@@ -498,7 +546,8 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     const double rstd = 1.0 / sqrt(var + 1e-5);
                     t = make_float2((float)rstd, (float)(-mm * rstd));
                 }
-                sts64(tab_u32 + i * 8, t);
+                // slot of channel c: [(c % 8) / 2][c / 8][c % 2] (see norm_split8)
+                sts64(tab_u32 + (uint32_t)(s * CIN + ((c & 7) >> 1) * (CIN / 4) + (c >> 3) * 2 + (c & 1)) * 8, t);
             }
             tab_n = n;
             named_bar_sync(1, C::PRODUCERS);
@@ -576,7 +625,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                                 const float a8[8] = {acc[h8 * 8 + 0], acc[h8 * 8 + 1], acc[h8 * 8 + 2], acc[h8 * 8 + 3],
                                                      acc[h8 * 8 + 4], acc[h8 * 8 + 5], acc[h8 * 8 + 6], acc[h8 * 8 + 7]};
                                 uint4 hi, lo;
-                                norm_split8(a8, tab_u32 + (c16 * 2 + h8) * 64, hi, lo);
+                                norm_split8(a8, tab_u32 + (c16 * 2 + h8) * 16, CIN * 2, hi, lo);
                                 store_chunk<C>(stage_u32, pos, c16 * 2 + h8, hi, lo);
                             }
                         }
@@ -655,7 +704,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     if (src) {
                         const float xv[8] = {buf[i][0].x, buf[i][0].y, buf[i][0].z, buf[i][0].w,
                                              buf[i][1].x, buf[i][1].y, buf[i][1].z, buf[i][1].w};
-                        norm_split8(xv, tab_u32 + (s * CIN + c.cc * C::KC + c8 * 8) * 8, hi, lo);
+                        norm_split8(xv, tab_u32 + (uint32_t)(s * CIN * 8 + (c.cc * C8 + c8) * 16), CIN * 2, hi, lo);
                     }
                     store_chunk<C>(stage_u32, pos, c8, hi, lo);
                 }
@@ -695,6 +744,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if (C::CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
     if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
