@@ -163,23 +163,23 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 }
 
 // y = leaky(x * scale + shift) split into fp16 hi / lo; eight values -> two 16-byte chunks.
-// The (scale, shift) table is laid out [pair j = 0..3][8-channel group][2 channels] so that the eight lanes that
-// handle the eight channel groups of one position read 128 contiguous bytes (no bank conflicts): the pairs of
-// channels 2j, 2j+1 of group c8 sit at tab + j * jstride + c8 * 16.  tab_u32 already includes c8 * 16.
+// The table holds one float4 (scale_a, scale_b, shift_a, shift_b) per channel PAIR, laid out [pair j = 0..3][8-channel
+// group] so that the eight lanes that handle the eight channel groups of one position read 128 contiguous bytes (no
+// bank conflicts): pair j of group c8 sits at tab + j * jstride + c8 * 16.  tab_u32 already includes c8 * 16.
+// Packed fp32 pairs (FFMA2 / FMUL2, sm_100) halve the issue slots of the arithmetic.
+__device__ __forceinline__ void norm_split_pair(float2 x, const float4 &tt, __half2 &h, __half2 &l) {
+    const float2 y = __ffma2_rn(x, make_float2(tt.x, tt.y), make_float2(tt.z, tt.w));
+    const float2 z = __fmul2_rn(y, make_float2(0.02f, 0.02f));
+    const float2 a = make_float2(fmaxf(y.x, z.x), fmaxf(y.y, z.y));  // LeakyReLU(0.02)
+    h = __floats2half2_rn(a.x, a.y);
+    const float2 d = __ffma2_rn(__half22float2(h), make_float2(-1.f, -1.f), a);  // exact: a - hi
+    l = __floats2half2_rn(d.x, d.y);
+}
 __device__ __forceinline__ void norm_split8(const float (&x)[8], uint32_t tab_u32, uint32_t jstride, uint4 &hi,
                                             uint4 &lo) {
     __half2 h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float4 tt = lds128(tab_u32 + j * jstride);
-        const float2 t0 = make_float2(tt.x, tt.y), t1 = make_float2(tt.z, tt.w);
-        float a = fmaf(x[2 * j], t0.x, t0.y), b = fmaf(x[2 * j + 1], t1.x, t1.y);
-        a = fmaxf(a, 0.02f * a);
-        b = fmaxf(b, 0.02f * b);
-        h[j] = __floats2half2_rn(a, b);
-        const float2 hf = __half22float2(h[j]);
-        l[j] = __floats2half2_rn(a - hf.x, b - hf.y);
-    }
+    for (int j = 0; j < 4; ++j) norm_split_pair(make_float2(x[2 * j], x[2 * j + 1]), lds128(tab_u32 + j * jstride), h[j], l[j]);
     hi = *(const uint4 *)h;
     lo = *(const uint4 *)l;
 }
@@ -211,7 +211,6 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     uint64_t *tempty_bar = tfull_bar + 2;            // [2]
     uint32_t *tmem_slot = (uint32_t *)(tempty_bar + 2);
     const uint32_t tab_u32 = smem_u32(extra + 512);     // float2 [NI][CIN] (scale, shift) of the source planes: <= 2 KB
-    const uint32_t w0s_u32 = smem_u32(extra + 2560);    // FIRST: float [9][32] conv0 weights (1152 B)
     const uint32_t patch_u32 = smem_u32(extra + 3840);  // FIRST: float [20][36] input pixels (2880 B) -> ends at 6720
 
     const int warp = threadIdx.x >> 5;
@@ -546,15 +545,25 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     const double rstd = 1.0 / sqrt(var + 1e-5);
                     t = make_float2((float)rstd, (float)(-mm * rstd));
                 }
-                // slot of channel c: [(c % 8) / 2][c / 8][c % 2] (see norm_split8)
-                sts64(tab_u32 + (uint32_t)(s * CIN + ((c & 7) >> 1) * (CIN / 4) + (c >> 3) * 2 + (c & 1)) * 8, t);
+                // channel c -> float4 [(c % 8) / 2][c / 8], scale in component c % 2, shift in 2 + c % 2 (see norm_split8)
+                const uint32_t slot = tab_u32 + (uint32_t)(s * CIN * 8 + (((c & 7) >> 1) * (CIN / 8) + (c >> 3)) * 16 + (c & 1) * 4);
+                sts32(slot, __float_as_uint(t.x));
+                sts32(slot + 8, __float_as_uint(t.y));
             }
             tab_n = n;
             named_bar_sync(1, C::PRODUCERS);
         };
         unsigned ait = 0;
         if constexpr (C::FIRST) {
-            for (int i = ptid; i < 9 * 32; i += C::PRODUCERS) sts32(w0s_u32 + i * 4, __float_as_uint(p.w0[i]));
+            // conv0 on CUDA cores, weight-stationary: a producer warp owns one group of 8 output channels and keeps
+            // its 72 weights in registers (as 36 channel pairs for FFMA2); a unit = (window position, channel group).
+            const int pw = warp - 8, cg = pw & 3, phalf = pw >> 2;
+            float2 wreg[9][4];
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    wreg[tp][j] = make_float2(__ldg(p.w0 + tp * 32 + cg * 8 + 2 * j), __ldg(p.w0 + tp * 32 + cg * 8 + 2 * j + 1));
             // the 20 x 36 input pixels of a window (conv0 halo on top of the conv1 halo) are fetched one item ahead
             constexpr int NPV = (20 * 36 + C::PRODUCERS - 1) / C::PRODUCERS;
             uint32_t pv[NPV];  // raw pixel bits; converted when they are written to the patch, one item later
@@ -593,47 +602,34 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 const int sa = ait % C::A_STAGES;
                 mbar_wait_bounded(&a_empty[sa], ((ait / C::A_STAGES) & 1u) ^ 1u);
                 const uint32_t stage_u32 = smem_base_u32 + sa * C::A_STAGE;
-#pragma unroll 1
-                for (int pos = ptid; pos < ((p.dbg & 1) ? 0 : C::WIN_POS); pos += C::PRODUCERS) {
+                float4 tt[4];  // (scale, shift) of this warp's 8 channels for the current image
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tt[j] = lds128(tab_u32 + (uint32_t)((j * (CIN / 8) + cg) * 16));
+#pragma unroll 2
+                for (int pos = phalf * 32 + lane; pos < ((p.dbg & 1) ? 0 : C::WIN_POS); pos += 64) {
                     const int wy = pos / C::PITCH, wx = pos - wy * C::PITCH;
                     const int y = y0 - 1 + wy, x = x0 - 1 + wx;
+                    uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
                     if (y >= 0 && y < 128 && x >= 0 && x < 128) {
-                        float in[9];
+                        float2 acc[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
                         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                            for (int dx = 0; dx < 3; ++dx)
-                                in[dy * 3 + dx] = lds32(patch_u32 + ((wy + dy) * 36 + wx + dx) * 4);
+                            for (int dx = 0; dx < 3; ++dx) {
+                                const float v = lds32(patch_u32 + ((wy + dy) * 36 + wx + dx) * 4);
+                                const float2 vv = make_float2(v, v);
 #pragma unroll
-                        for (int c16 = 0; c16 < 2; ++c16) {
-                            float acc[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-#pragma unroll
-                            for (int tp = 0; tp < 9; ++tp) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const float4 wv = lds128(w0s_u32 + (tp * 32 + c16 * 16 + q * 4) * 4);
-                                    acc[q * 4 + 0] = fmaf(in[tp], wv.x, acc[q * 4 + 0]);
-                                    acc[q * 4 + 1] = fmaf(in[tp], wv.y, acc[q * 4 + 1]);
-                                    acc[q * 4 + 2] = fmaf(in[tp], wv.z, acc[q * 4 + 2]);
-                                    acc[q * 4 + 3] = fmaf(in[tp], wv.w, acc[q * 4 + 3]);
-                                }
+                                for (int j = 0; j < 4; ++j) acc[j] = __ffma2_rn(vv, wreg[dy * 3 + dx][j], acc[j]);
                             }
+                        __half2 h[4], l[4];
 #pragma unroll
-                            for (int h8 = 0; h8 < 2; ++h8) {
-                                const float a8[8] = {acc[h8 * 8 + 0], acc[h8 * 8 + 1], acc[h8 * 8 + 2], acc[h8 * 8 + 3],
-                                                     acc[h8 * 8 + 4], acc[h8 * 8 + 5], acc[h8 * 8 + 6], acc[h8 * 8 + 7]};
-                                uint4 hi, lo;
-                                norm_split8(a8, tab_u32 + (c16 * 2 + h8) * 16, CIN * 2, hi, lo);
-                                store_chunk<C>(stage_u32, pos, c16 * 2 + h8, hi, lo);
-                            }
-                        }
-                    } else {
-                        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                        for (int c8 = 0; c8 < 4; ++c8) store_chunk<C>(stage_u32, pos, c8, z, z);
+                        for (int j = 0; j < 4; ++j) norm_split_pair(acc[j], tt[j], h[j], l[j]);
+                        hi = *(const uint4 *)h;
+                        lo = *(const uint4 *)l;
                     }
+                    store_chunk<C>(stage_u32, pos, cg, hi, lo);
                 }
                 fence_proxy_async();
                 mbar_arrive(&a_full[sa]);

@@ -37,6 +37,12 @@ struct __align__(8) Entry {
     int idx;
 };
 
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ bool beats(float da, long long ia, float db, long long ib) {
     return (da > db) || (da == db && ia < ib);
 }
@@ -180,7 +186,10 @@ topk_kernel(const __grid_constant__ CUtensorMap dict_map, const TopkParams p) {
                 const int s = cit % kStages;
                 const unsigned ph = (cit / kStages) & 1u;
                 mbar_wait(&full_bar[s], ph);
-                const float4 *dt = (const float4 *)(smem + S::off_dtile + s * kTileBytes);
+                // explicit shared-window addresses: the manually aligned smem pointer has lost its address space and
+                // would compile to generic 64-bit loads
+                const uint32_t dt_u32 = smem_u32(smem + S::off_dtile + s * kTileBytes);
+                const uint32_t qt_u32 = smem_u32(qtile);
 
                 float acc[TQ][8];
 #pragma unroll
@@ -192,10 +201,10 @@ topk_kernel(const __grid_constant__ CUtensorMap dict_map, const TopkParams p) {
                 for (int c = 0; c < 4; ++c) {
                     float4 dv[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dv[i] = dt[(dg + 16 * i) * 4 + (c ^ swz)];
+                    for (int i = 0; i < 8; ++i) dv[i] = lds_f4(dt_u32 + (uint32_t)(((dg + 16 * i) * 4 + (c ^ swz)) * 16));
 #pragma unroll
                     for (int qi = 0; qi < TQ; ++qi) {
-                        const float4 qv = *(const float4 *)(qtile + (((warp * TQ + qi) * 2 + qg) * kD) + c * 4);
+                        const float4 qv = lds_f4(qt_u32 + (uint32_t)(((((warp * TQ + qi) * 2 + qg) * kD) + c * 4) * 4));
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             float a = acc[qi][i];
@@ -211,52 +220,48 @@ topk_kernel(const __grid_constant__ CUtensorMap dict_map, const TopkParams p) {
                 if (lane == 0) mbar_arrive(&empty_bar[s]);
                 if (tid == 0 && t + kStages - 1 < ntiles) issue_tile(t + kStages - 1);
 
-                // ---- selection: fast reject against tau, slow path only when something survives
+                // ---- selection: fast reject against tau; survivors are found with warp ballots and inserted one by
+                // one, so the cost is proportional to the number of survivors (a few per query per tile once tau
+                // has warmed up), not to the tile size.  For one query the visiting order is (i, lane) ascending =
+                // row ascending, which is what the strict "dot > tau" rule needs for the lower-row-wins tie order.
+                // Per lane and query: the best of its 8 rows.  One vote tells whether the tile can be skipped; if
+                // not, one ballot per query slot finds the lanes to look at, and only those cost a ballot per row.
+                float best[TQ];
                 bool hit = false;
 #pragma unroll
-                for (int qi = 0; qi < TQ; ++qi)
+                for (int qi = 0; qi < TQ; ++qi) {
+                    float b = acc[qi][0];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) hit |= acc[qi][i] > tau[qi];
-
+                    for (int i = 1; i < 8; ++i) b = fmaxf(b, acc[qi][i]);
+                    best[qi] = b;
+                    hit |= b > tau[qi];
+                }
                 if (__any_sync(0xffffffffu, hit)) {
                     const long long row_base = (tile0 + t) * kTileRows;  // shard-local row of tile row 0
                     long long valid_ll = p.N - row_base;
                     const int valid = valid_ll > kTileRows ? kTileRows : (int)valid_ll;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = dg + 16 * i;
-                        bool pushed = false;
-                        if (row < valid) {
+                    for (int qi = 0; qi < TQ; ++qi) {
+                        if (__ballot_sync(0xffffffffu, best[qi] > tau[qi]) == 0u) continue;
 #pragma unroll
-                            for (int qi = 0; qi < TQ; ++qi) {
-                                if (acc[qi][i] > tau[qi]) {
-                                    const int ql = wq0 + qg * TQ + qi;
-                                    const int slot = atomicAdd(&cnt[ql], 1);
-                                    Entry e;
-                                    e.dot = acc[qi][i];
-                                    e.idx = (int)(row_base + row);
-                                    cands[ql * kCandCap + slot] = e;
-                                    pushed = true;
-                                }
-                            }
-                        }
-                        if (__any_sync(0xffffffffu, pushed)) {
-                            __syncwarp();
-                            for (int ql = wq0; ql < wq0 + QPW; ++ql) {
-                                const int c = cnt[ql];
-                                if (c == 0) continue;
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = dg + 16 * i;
+                            unsigned m = __ballot_sync(0xffffffffu, row < valid && acc[qi][i] > tau[qi]);
+                            while (m) {  // warp-uniform
+                                const int src = __ffs(m) - 1;
+                                m &= m - 1;
+                                const float cd = __shfl_sync(0xffffffffu, acc[qi][i], src);
+                                const int sq = src >> 4;  // which half of the warp's queries the source lane serves
+                                const int ql = wq0 + sq * TQ + qi;
+                                // tau of that query may have risen since the ballot (earlier survivor of this tile)
+                                const float cur_tau = __shfl_sync(0xffffffffu, tau[qi], sq << 4);
+                                if (!(cd > cur_tau)) continue;
                                 Entry e = lists[ql * kListLen + lane];
-                                for (int j = 0; j < c; ++j) {
-                                    const Entry cd = cands[ql * kCandCap + j];
-                                    warp_insert<int>(e.dot, e.idx, cd.dot, cd.idx, lane);
-                                }
+                                warp_insert<int>(e.dot, e.idx, cd, (int)(row_base + (src & 15) + 16 * i), lane);
                                 lists[ql * kListLen + lane] = e;
-                                if (lane == p.k - 1) tau_s[ql] = e.dot;
-                                if (lane == 0) cnt[ql] = 0;
+                                const float kth = __shfl_sync(0xffffffffu, e.dot, p.k - 1);  // -inf until k entries
+                                if (qg == sq) tau[qi] = kth;
                             }
-                            __syncwarp();
-#pragma unroll
-                            for (int qi = 0; qi < TQ; ++qi) tau[qi] = tau_s[wq0 + qg * TQ + qi];
                         }
                     }
                 }

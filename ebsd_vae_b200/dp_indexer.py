@@ -50,7 +50,7 @@ class DiffractionPatternIndexer:
     """Indexes diffraction patterns using the VAE encoder and the GPU latent dictionary."""
 
     #: patterns encoded per native call inside build_dictionary / encode_patterns_batch (host staging granularity)
-    ENCODE_CHUNK = 4096
+    ENCODE_CHUNK = 2368
 
     def __init__(self, model, db: LatentVectorDatabase | None = None, config: IndexerConfig | None = None) -> None:
         self.config = config if config is not None else IndexerConfig()
@@ -73,6 +73,7 @@ class DiffractionPatternIndexer:
         self.model.eval()
         self.model.to(self.device)
         self._engine: EncoderEngine | None = None
+        self._copy_stream: torch.cuda.Stream | None = None
 
     # ------------------------------------------------------------------ encoder plumbing
     @property
@@ -84,16 +85,38 @@ class DiffractionPatternIndexer:
                 self._engine = EncoderEngine(self.model.state_dict(), self.device)
         return self._engine
 
-    def _encode_u8_host(self, u8: np.ndarray) -> torch.Tensor:
-        """uint8 [B,128,128] on the host -> mu [B,16] on the device (pinned staging, chunked)."""
-        outs = []
-        for a in range(0, len(u8), self.ENCODE_CHUNK):
-            chunk = torch.from_numpy(u8[a : a + self.ENCODE_CHUNK])
-            dev = chunk.pin_memory().to(self.device, non_blocking=True)
-            outs.append(self.engine.encode(dev))
-        if not outs:
+    def _encode_host_tensor(self, t: torch.Tensor) -> torch.Tensor:
+        """Host tensor [B,128,128] (uint8 or float32) -> mu [B,16] on the device.
+
+        The host -> device copy is pipelined against the encoder: slices of ``ENCODE_CHUNK`` patterns are copied
+        on a side stream into one device buffer while the compute stream encodes the slices that have already
+        landed (pinned sources copy asynchronously; pageable ones still work, just without the overlap).
+        """
+        b = t.shape[0]
+        if b == 0:
             return torch.empty((0, self.config.latent_dim), dtype=torch.float32, device=self.device)
-        return outs[0] if len(outs) == 1 else torch.cat(outs)
+        t = t.contiguous()
+        compute = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        dev = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+        mu = torch.empty((b, self.config.latent_dim), dtype=torch.float32, device=self.device)
+        self._copy_stream.wait_stream(compute)  # `dev` was allocated on the compute stream
+        events = []
+        with torch.cuda.stream(self._copy_stream):
+            for a in range(0, b, self.ENCODE_CHUNK):
+                dev[a : a + self.ENCODE_CHUNK].copy_(t[a : a + self.ENCODE_CHUNK], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                events.append(ev)
+        for i, a in enumerate(range(0, b, self.ENCODE_CHUNK)):
+            compute.wait_event(events[i])
+            mu[a : a + self.ENCODE_CHUNK] = self.engine.encode(dev[a : a + self.ENCODE_CHUNK])
+        return mu
+
+    def _encode_u8_host(self, u8: np.ndarray) -> torch.Tensor:
+        """uint8 [B,128,128] on the host -> mu [B,16] on the device."""
+        return self._encode_host_tensor(torch.from_numpy(np.ascontiguousarray(u8)))
 
     def _encode_any(self, patterns) -> torch.Tensor:
         """Reference input rules (dp_indexer.py:124-131, 150-169): ndarrays go through the transform, tensors bypass it."""
@@ -110,9 +133,11 @@ class DiffractionPatternIndexer:
             t = t[:, 0]
         elif t.dim() != 3:
             raise AssertionError(f"Expected 4D tensor, got {t.dim()}D")
-        t = t.to(self.device)
         if t.dtype != torch.uint8:
             t = t.to(torch.float32)
+        if t.device.type == "cpu":
+            return self._encode_host_tensor(t)
+        t = t.to(self.device)
         outs = [self.engine.encode(t[a : a + self.ENCODE_CHUNK]) for a in range(0, t.shape[0], self.ENCODE_CHUNK)]
         return outs[0] if len(outs) == 1 else torch.cat(outs)
 
