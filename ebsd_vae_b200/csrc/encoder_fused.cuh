@@ -62,7 +62,10 @@ struct FusedCfg {
     static constexpr int A_STAGES = 2;
     // output staging for the TMA stores: per epilogue warp one [32 or 8 rows][128 B] box, 128B-swizzled
     static constexpr int WSTG = POOL ? 1024 : 4096;
-    static constexpr int NSB = (!POOL && RESIDENT_B) ? 2 : 1; // staging buffers per warp
+    // COUT = 32 with several tiles per item (the front end): the epilogue walks 16-channel halves outside the tile
+    // loop so that the plane sums stay in registers across the NT tiles; every tile then needs its own box
+    static constexpr bool ACCUM = COUT == 32 && NT > 1;
+    static constexpr int NSB = ACCUM ? NT : ((!POOL && RESIDENT_B) ? 2 : 1);  // staging boxes per warp
     static constexpr int STAGING = 4 * NSB * WSTG;
     static constexpr int EXTRA = 8192 + STAGING;             // barriers, tables, conv0 patch | staging
     static constexpr int B_FIT = (226 * 1024 - 1024 - EXTRA - A_STAGES * A_STAGE) / B_TILE;
@@ -382,8 +385,18 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         for (int cb = 0; cb < NCB; ++cb)
 #pragma unroll
             for (int s = 0; s < C::NI; ++s) acc1[cb][s] = acc2[cb][s] = 0.f;
+        float accum_lo = 0.f, accum_hi = 0.f;  // ACCUM: lane c < 16: sum of channel c (lo) / 16 + c (hi); lanes >= 16: squares
         int cur_n = -1;
         auto flush = [&]() {
+            if (C::ACCUM) {
+                if (cur_n >= 0 && cur_n < p.nimg) {
+                    double *dst = p.sums + ((long long)cur_n * COUT + (lane & 15)) * 2 + (lane >> 4);
+                    atomicAdd(dst, (double)accum_lo);
+                    atomicAdd(dst + 32, (double)accum_hi);
+                }
+                accum_lo = accum_hi = 0.f;
+                return;
+            }
             if (cur_n >= 0) {
 #pragma unroll
                 for (int s = 0; s < C::NI; ++s) {
@@ -425,6 +438,64 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
             mbar_wait_bounded(&tfull_bar[buf], ((unsigned)j >> 1) & 1u);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * C::ACC_COLS);
+            if constexpr (C::ACCUM) {
+                static_assert(!C::ACCUM || (POOL && C::NI == 1), "the accumulating epilogue is written for the pooled front end");
+                // all boxes of the previous item have been read by their TMA stores before they are overwritten
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+#pragma unroll 1
+                for (int hf = 0; hf < ((p.dbg & 4) ? 0 : 2); ++hf) {
+                    float z[32];  // [0,16): sums, [16,32): sums of squares of channels hf*16 + i over the item's tiles
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) z[i] = 0.f;
+#pragma unroll 1
+                    for (int t = 0; t < C::NT; ++t) {
+                        float v[16], w[16];
+                        tmem_ld16(t_row + t * 2 * COUT + hf * 16, v);
+                        tmem_ld16(t_row + t * 2 * COUT + COUT + hf * 16, w);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            v[i] = valid ? v[i] + w[i] : 0.f;
+                            z[i] += v[i];
+                            z[16 + i] = fmaf(v[i], v[i], z[16 + i]);
+                        }
+                        // 2x2 max: transposing butterfly, 16 -> 8 -> 4 channels per lane
+                        float r[8], o[4];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float send = a_par ? v[i] : v[8 + i];
+                            const float keep = a_par ? v[8 + i] : v[i];
+                            r[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float send = b_par ? r[i] : r[4 + i];
+                            const float keep = b_par ? r[4 + i] : r[i];
+                            o[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, PV));
+                        }
+                        const uint32_t stg = stg_u32 + (uint32_t)(t * C::WSTG);
+                        const int ch = hf * 4 + a_par * 2 + b_par;  // 16-byte chunk of this lane's 4 channels
+                        sts128(stg + (uint32_t)(prow * 128) + (uint32_t)((ch ^ (prow & 7)) << 4),
+                               make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])));
+                        if (hf == 1) {
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0 && n < p.nimg && !(p.dbg & 16)) {
+                                tma_store_4d(&map_out, stg, 0, (x0 + 8 * t) >> 1, (y0 + 4 * quarter) >> 1, n);
+                                bulk_commit();
+                            }
+                        }
+                    }
+                    if (!(p.dbg & 8)) {
+                        // one 32-wide transposing reduction serves both quantities: lane c < 16 ends up with the sum
+                        // of channel hf*16 + c, lane 16 + c with its sum of squares
+                        const float red = warp_transpose_reduce32(z, lane);
+                        if (hf == 0) accum_lo += red;
+                        else accum_hi += red;
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int t = 0; t < ((p.dbg & 4) ? 0 : C::NT); ++t) {
 #pragma unroll
@@ -505,6 +576,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                         }
                     }
                 }
+            }
             }
             tc_fence_before();
             __syncwarp();
