@@ -474,6 +474,27 @@ int make_out_map(CUtensorMap *map, const float *base, int cout, int wo, int nimg
     return EBSD_OK;
 }
 
+// fp32 [nimg,W,W,CIN] source as (c, x, y, n) for L2 prefetches of whole windows (no shared-memory destination)
+int make_src_map(CUtensorMap *map, const float *base, int cin, int w, int nimg, int bx, int by, int bn) {
+    tensormap_encode_fn encode = get_tensormap_encode();
+    if (!encode) {
+        set_error("encoder: cuTensorMapEncodeTiled entry point not available");
+        return EBSD_ERR_CUDA;
+    }
+    const cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)w, (cuuint64_t)nimg};
+    const cuuint64_t gstride[3] = {(cuuint64_t)cin * 4, (cuuint64_t)w * cin * 4, (cuuint64_t)w * w * cin * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)cin, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bn};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("encoder: cuTensorMapEncodeTiled(raw source) failed with %d", (int)cr);
+        return EBSD_ERR_CUDA;
+    }
+    return EBSD_OK;
+}
+
 template <int CIN, int COUT, int W, int SRC, bool POOL>
 int launch_fused(const ebsd_encoder *enc, int layer, const void *src, const double *src_sums, int src_plane,
                  float *raw, double *sums, int nimg, cudaStream_t st) {
@@ -484,8 +505,16 @@ int launch_fused(const ebsd_encoder *enc, int layer, const void *src, const doub
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
-    CUtensorMap map_out;
+    CUtensorMap map_out, map_src;
     int rc;
+    if (SRC == SRC_RAW) {
+        // the window a work item reads: (all channels, PITCH or 8 columns, WIN_H or 8 rows, NI images)
+        if (C::NI == 1) rc = make_src_map(&map_src, (const float *)src, CIN, W, nimg, C::PITCH, C::WIN_H, 1);
+        else rc = make_src_map(&map_src, (const float *)src, CIN, W, nimg, W, W, C::NI);
+        if (rc) return rc;
+    } else {
+        memset(&map_src, 0, sizeof(map_src));
+    }
     if (C::NI == 1) rc = make_out_map(&map_out, raw, COUT, POOL ? W / 2 : W, nimg, POOL ? 4 : 8, POOL ? 2 : 4, 1);
     else rc = make_out_map(&map_out, raw, COUT, POOL ? W / 2 : W, nimg, POOL ? 4 : 8, POOL ? 1 : 2, 2);
     if (rc) return rc;
@@ -528,7 +557,7 @@ int launch_fused(const ebsd_encoder *enc, int layer, const void *src, const doub
     int grid = (p.nitems + per - 1) / per;
     grid = (grid + C::CL - 1) / C::CL * C::CL;
     cfg.gridDim = dim3(grid);
-    EBSD_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_fused_kernel<CIN, COUT, W, SRC, POOL>, enc->w_map_fused[layer], map_out, p));
+    EBSD_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_fused_kernel<CIN, COUT, W, SRC, POOL>, enc->w_map_fused[layer], map_out, map_src, p));
     EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }

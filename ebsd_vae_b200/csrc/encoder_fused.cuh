@@ -109,6 +109,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t sm
                  "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
+// Fire-and-forget L2 prefetch of a 4-D box (out-of-range coordinates are simply skipped by the TMA unit).
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -199,7 +205,8 @@ __device__ __forceinline__ void store_chunk(uint32_t stage_u32, int pos, int c8,
 template <int CIN, int COUT, int W, int SRC, bool POOL>
 __global__ void __launch_bounds__(512, 1)
 conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
-                     const FusedParams p) {
+                     const __grid_constant__ CUtensorMap map_src, const FusedParams p) {
+    // map_src (SRC_RAW only): the source raw tensor (c, x, y, n) with box = one window; used for L2 prefetches
     // map_w: box = [KC, 2*COUT / CL] rows of the packed weights (the whole tile when CL = 1)
     using C = FusedCfg<CIN, COUT, W, SRC, POOL>;
     extern __shared__ uint8_t smem_raw[];
@@ -253,16 +260,44 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                                    : (item_begin + per_cta < p.nitems ? item_begin + per_cta : p.nitems);
 
     if (warp == 0) {
-        // ===================== weight loads (TMA)
+        // ===================== weight loads (TMA) + L2 prefetch of the windows the producers will read
         if (elect_one_sync()) {
+            constexpr int PF = 4;  // items ahead: the producers themselves run up to A_STAGES items ahead of the MMAs
+            auto prefetch_item = [&](int item) {
+                if (C::FIRST || item >= item_end || item >= p.nitems) return;
+                int n, y0, x0;
+                if (C::NI == 1) {
+                    n = item / C::ITEMS_PER_IMAGE;
+                    const int r = item - n * C::ITEMS_PER_IMAGE;
+                    const int yb = r / C::ITEMS_X;
+                    y0 = yb * 16 - 1;
+                    x0 = (r - yb * C::ITEMS_X) * 8 * C::NT - 1;
+                } else {
+                    n = item * 2;
+                    y0 = 0;
+                    x0 = 0;
+                }
+                tma_prefetch_l2_4d(&map_src, 0, x0, y0, n);
+            };
+            for (int j = 0; j < PF; ++j) prefetch_item(item_begin + j);
             if (C::RESIDENT_B) {
                 for (int kb = 0; kb < 9 * C::NCHUNK; ++kb) {
                     mbar_expect_tx(&b_full[kb], C::B_TILE);
                     tma_load_2d(smem_b + kb * C::B_TILE, &map_w, 0, kb * 2 * COUT, &b_full[kb]);
                 }
+                if (!C::FIRST) {
+                    // pace the prefetches with the windows becoming ready (a_full is only observed here)
+                    unsigned ait = 0;
+                    for (int item = item_begin; item < item_end; ++item)
+                        for (int cc = 0; cc < C::NCHUNK; ++cc, ++ait) {
+                            mbar_wait_bounded(&a_full[ait % C::A_STAGES], (ait / C::A_STAGES) & 1u);
+                            if (cc == 0) prefetch_item(item + PF);
+                        }
+                }
             } else {
                 unsigned bit = 0;
-                for (int item = item_begin; item < item_end; ++item)
+                for (int item = item_begin; item < item_end; ++item) {
+                    prefetch_item(item + PF);
                     for (int cc = 0; cc < C::NCHUNK; ++cc)
                         for (int tap = 0; tap < 9; ++tap, ++bit) {
                             const int sb = bit % C::B_STAGES;
@@ -278,6 +313,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                                                smem_u32(&b_full[sb]), (uint16_t)((1u << C::CL) - 1));
                             }
                         }
+                }
             }
         }
     } else if (warp == 1) {
