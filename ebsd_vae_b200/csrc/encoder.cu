@@ -446,11 +446,11 @@ FusedWorkspace carve_fused(void *workspace, size_t chunk, size_t sub) {
 }
 
 // rows of the packed weights one CTA fetches per (tap, K chunk): the whole [w_hi; w_lo] tile, or its 1/CL slice
-// when the block streams its weights through a cluster (FusedCfg::RESIDENT_B / CL)
+// when the block runs as a CTA pair (FusedCfg::RESIDENT_B / PAIR)
 int fused_weight_box_rows(int layer) {
     const int cin = kPlan[layer].cin, cout = kPlan[layer].cout, kc = cin < 64 ? cin : 64;
     const bool resident = 9 * (cin / kc) * 2 * cout * kc * 2 <= 80 * 1024;
-    return resident ? 2 * cout : 2 * cout / EBSD_CL;
+    return resident || !EBSD_PAIR ? 2 * cout : cout;  // CTA pair: each CTA holds half of the stacked rows
 }
 
 // fp32 [nimg,Wo,Wo,COUT] output as a 4-D tensor (c, x, y, n); box = (32 channels, bx, by, bn), 128B-swizzled in smem

@@ -29,8 +29,13 @@ namespace ebsd {
 
 enum FusedSrc { SRC_U8 = 0, SRC_F32 = 1, SRC_RAW = 2 };
 
-#ifndef EBSD_CL
-#define EBSD_CL 2   // cluster size of the blocks whose weights are streamed (1, 2 or 4)
+// 1 = the blocks whose weights are streamed run as CTA pairs (tcgen05 cta_group::2, four-term product).  Correct
+// (the per-block parity tests pass in both modes) but MEASURED SLOWER on B200: under tensor load the chip is
+// power-limited (~1.4-1.7 GHz), the single-CTA three-term blocks already run at ~80 % of their clock-adjusted MMA
+// floor, and the fourth term costs 33 % more tensor work than the halved weight traffic saves
+// (profiles/README.md).  Kept as a build option: make EXTRA=-DEBSD_PAIR=1.
+#ifndef EBSD_PAIR
+#define EBSD_PAIR 0
 #endif
 
 template <int CIN_, int COUT_, int W_, int SRC_, bool POOL_>
@@ -54,11 +59,15 @@ struct FusedCfg {
     static constexpr int A_STAGE = 2 * A_PLANE;              // hi + lo
     static constexpr int B_TILE = 2 * COUT * ROWB;           // [w_hi; w_lo] of one (tap, K chunk)
     static constexpr bool RESIDENT_B = 9 * NCHUNK * B_TILE <= 80 * 1024;
-    // Streamed weights: a cluster of CL CTAs shares every [w_hi; w_lo] tile -- each CTA fetches 1/CL of it and
-    // multicasts that slice into all CL shared memories, so the L2 -> SM weight traffic drops by CL.
-    static constexpr int CL = RESIDENT_B ? 1 : EBSD_CL;
-    static constexpr int B_SLICE_ROWS = 2 * COUT / CL;
-    static constexpr int B_SLICE = B_TILE / CL;
+    // Streamed weights (the 64->64 ... 128->128 blocks) make the L2 -> SM weight traffic the limiter: one [w_hi; w_lo]
+    // tile feeds only 128 output positions.  Those blocks therefore run as CTA PAIRS (tcgen05 cta_group::2, M = 256):
+    // each CTA builds the window of its own work item and holds HALF of every weight tile (CTA 0 the w_hi rows, CTA 1
+    // the w_lo rows), so the weight bytes per SM halve and the ring is twice as deep.  Both planes use the same B
+    // operand (N = 2*COUT), i.e. the full four-term product a_hi*w_hi + a_hi*w_lo + a_lo*w_hi + a_lo*w_lo.
+    static constexpr bool PAIR = !RESIDENT_B && EBSD_PAIR;
+    static constexpr int CL = PAIR ? 2 : 1;                  // cluster size
+    static constexpr int B_CTA = B_TILE / CL;                // weight bytes one CTA holds per (tap, K chunk)
+    static constexpr int B_CTA_ROWS = 2 * COUT / CL;
     static constexpr int A_STAGES = 2;
     // output staging for the TMA stores: per epilogue warp one [32 or 8 rows][128 B] box, 128B-swizzled
     static constexpr int WSTG = POOL ? 1024 : 4096;
@@ -68,9 +77,9 @@ struct FusedCfg {
     static constexpr int NSB = ACCUM ? NT : ((!POOL && RESIDENT_B) ? 2 : 1);  // staging boxes per warp
     static constexpr int STAGING = 4 * NSB * WSTG;
     static constexpr int EXTRA = 8192 + STAGING;             // barriers, tables, conv0 patch | staging
-    static constexpr int B_FIT = (226 * 1024 - 1024 - EXTRA - A_STAGES * A_STAGE) / B_TILE;
-    static constexpr int B_STAGES = RESIDENT_B ? 9 * NCHUNK : (B_FIT > 6 ? 6 : B_FIT);
-    static constexpr int B_BYTES = B_STAGES * B_TILE;
+    static constexpr int B_FIT = (226 * 1024 - 1024 - EXTRA - A_STAGES * A_STAGE) / B_CTA;
+    static constexpr int B_STAGES = RESIDENT_B ? 9 * NCHUNK : (B_FIT > 8 ? 8 : B_FIT);
+    static constexpr int B_BYTES = B_STAGES * B_CTA;
     static constexpr int ACC_COLS = NT * 2 * COUT;           // TMEM columns of one work item
     static constexpr int TMEM_COLS = 512;
     static constexpr int SMEM_BYTES = 1024 + A_STAGES * A_STAGE + B_BYTES + EXTRA;
@@ -122,18 +131,69 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap *map, int c0, int c1, uint32_t bar,
-                                               uint16_t cta_mask) {
+// ---- CTA-pair (cta_group::2) helpers.  `bar` arguments are shared-window addresses of the issuing CTA; the leader
+// (cluster rank 0) owns the barriers the MMA issuer waits on, so followers signal the leader's copy.
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+// wait with cluster-scope acquire: the arrivals come from the peer CTA's threads (bounded like mbar_wait_bounded)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000ll) {
+            printf("ebsd encoder: pair mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// this CTA's half of a weight tile; the transaction bytes are credited to the LEADER's barrier (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap *map, int c0, int c1,
+                                                 uint32_t leader_bar) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::
-            "r"(smem_dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask)
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(smem_dst), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at the same offset in BOTH CTAs of the pair once the preceding MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                      smem_u32(bar)),
-                 "h"(cta_mask)
+                 "h"((uint16_t)3)
                  : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__host__ __device__ constexpr uint32_t umma_idesc_f16_m256(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -228,33 +288,41 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::A_STAGES; ++s) {
-            mbar_init(&a_full[s], C::PRODUCERS);
+            // PAIR: one arrival per producer warp of BOTH CTAs, collected on the leader's barrier
+            mbar_init(&a_full[s], C::PAIR ? 2 * (C::PRODUCERS / 32) : C::PRODUCERS);
             mbar_init(&a_empty[s], 1);
         }
         for (int s = 0; s < C::B_STAGES; ++s) {
             mbar_init(&b_full[s], 1);
-            mbar_init(&b_empty[s], C::CL);   // one tcgen05.commit from every CTA of the cluster
+            mbar_init(&b_empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull_bar[b], 1);
-            mbar_init(&tempty_bar[b], 4);
+            mbar_init(&tempty_bar[b], C::PAIR ? 8 : 4);  // PAIR: the epilogue warps of both CTAs release the leader
         }
         mbar_fence_init();
         tma_prefetch_desc(&map_w);
         tma_prefetch_desc(&map_out);
     }
-    if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if (C::PAIR) {
+        __syncthreads();
+        cluster_sync_all();  // both CTAs are resident and their barriers initialised before the pair allocates TMEM
+        if (warp == 2) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+    } else {
+        if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    }
     tc_fence_before();
     __syncthreads();
-    if (C::CL > 1) cluster_sync_all();  // peers' barriers are initialised before anything is multicast to them
+    if (C::PAIR) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t cta_rank = C::PAIR ? cluster_ctarank() : 0u;
 
     // contiguous item range per CTA: consecutive items belong to the same image, so plane statistics are
     // flushed once per image per warp instead of once per tile
     const int per_cta = (p.nitems + (int)gridDim.x - 1) / (int)gridDim.x;
     const int item_begin = (int)blockIdx.x * per_cta;
-    // CL > 1: every CTA of a cluster runs the same number of items (the weight ring advances in lock step); items
+    // PAIR: both CTAs of a pair run the same number of items (one M = 256 MMA stream serves both); items
     // beyond nitems decode to images >= nimg, which every role already treats as "nothing to load or store".
     const int item_end = C::CL > 1 ? item_begin + per_cta
                                    : (item_begin + per_cta < p.nitems ? item_begin + per_cta : p.nitems);
@@ -302,23 +370,25 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                         for (int tap = 0; tap < 9; ++tap, ++bit) {
                             const int sb = bit % C::B_STAGES;
                             mbar_wait_bounded(&b_empty[sb], ((bit / C::B_STAGES) & 1u) ^ 1u);
-                            mbar_expect_tx(&b_full[sb], C::B_TILE);
-                            if (C::CL == 1) {
+                            if (!C::PAIR) {
+                                mbar_expect_tx(&b_full[sb], C::B_TILE);
                                 tma_load_2d(smem_b + sb * C::B_TILE, &map_w, 0, (tap * C::NCHUNK + cc) * 2 * COUT,
                                             &b_full[sb]);
                             } else {
-                                const int rank = (int)cluster_ctarank();
-                                tma_load_2d_mc(smem_u32(smem_b + sb * C::B_TILE + rank * C::B_SLICE), &map_w, 0,
-                                               (tap * C::NCHUNK + cc) * 2 * COUT + rank * C::B_SLICE_ROWS,
-                                               smem_u32(&b_full[sb]), (uint16_t)((1u << C::CL) - 1));
+                                // this CTA's half of the tile (rank 0: w_hi rows, rank 1: w_lo rows); the leader's
+                                // barrier collects the bytes of both halves
+                                if (cta_rank == 0) mbar_expect_tx(&b_full[sb], C::B_TILE);
+                                tma_load_2d_pair(smem_u32(smem_b + sb * C::B_CTA), &map_w, 0,
+                                                 (tap * C::NCHUNK + cc) * 2 * COUT + (int)cta_rank * C::B_CTA_ROWS,
+                                                 map_to_cta(smem_u32(&b_full[sb]), 0));
                             }
                         }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer
-        if (elect_one_sync()) {
+        // ===================== MMA issuer (PAIR: the leader CTA issues for both)
+        if (cta_rank == 0 && elect_one_sync()) {
             constexpr uint32_t idesc_n2 = umma_idesc_f16(2 * COUT);
             constexpr uint32_t idesc_n1 = umma_idesc_f16(COUT);
             if (C::RESIDENT_B) {
@@ -329,12 +399,14 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
             int j = 0;
             for (int item = item_begin; item < item_end; ++item, ++j) {
                 const int buf = j & 1;
-                mbar_wait_bounded(&tempty_bar[buf], (((unsigned)j >> 1) & 1u) ^ 1u);
+                if (C::PAIR) mbar_wait_cluster(&tempty_bar[buf], (((unsigned)j >> 1) & 1u) ^ 1u);
+                else mbar_wait_bounded(&tempty_bar[buf], (((unsigned)j >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_item = tmem_base + (uint32_t)(buf * C::ACC_COLS);
                 for (int cc = 0; cc < C::NCHUNK; ++cc, ++ait) {
                     const int sa = ait % C::A_STAGES;
-                    mbar_wait_bounded(&a_full[sa], (ait / C::A_STAGES) & 1u);
+                    if (C::PAIR) mbar_wait_cluster(&a_full[sa], (ait / C::A_STAGES) & 1u);
+                    else mbar_wait_bounded(&a_full[sa], (ait / C::A_STAGES) & 1u);
                     tc_fence_after();
                     const uint32_t win_hi = smem_u32(smem + sa * C::A_STAGE);
                     const uint32_t win_lo = win_hi + C::A_PLANE;
@@ -367,7 +439,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                                              umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_lo + shift + t * 8 * C::ROWB + k * 32),
                                              umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_n1, 1u);
                         }
-                    } else {
+                    } else if (!C::PAIR) {
 #pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap, ++bit) {
                             const int dy = tap / 3, dx = tap - dy * 3;
@@ -391,13 +463,43 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                                     if (!(p.dbg & 2)) umma_f16(d_item + t * 2 * COUT,
                                              umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_lo + shift + t * 8 * C::ROWB + k * 32),
                                              umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_n1, 1u);
-                            if (C::CL == 1) umma_commit(&b_empty[sb]);
-                            else umma_commit_mc(&b_empty[sb], (uint16_t)((1u << C::CL) - 1));
+                            umma_commit(&b_empty[sb]);
+                        }
+                    } else {
+                        // CTA pair: M = 256 (this CTA's window rows + the peer's), N = 2*COUT with half of the weight
+                        // rows in each CTA; the hi and the lo plane use the same B operand (four-term product)
+                        constexpr uint32_t idesc_pair = umma_idesc_f16_m256(2 * COUT);
+#pragma unroll 1
+                        for (int tap = 0; tap < 9; ++tap, ++bit) {
+                            const int dy = tap / 3, dx = tap - dy * 3;
+                            const uint32_t shift = (uint32_t)((dy * C::PITCH + dx) * C::ROWB);
+                            const int sb = bit % C::B_STAGES;
+                            mbar_wait_bounded(&b_full[sb], (bit / C::B_STAGES) & 1u);
+                            tc_fence_after();
+                            const uint32_t b_w = smem_u32(smem_b + sb * C::B_CTA);
+#pragma unroll
+                            for (int t = 0; t < C::NT; ++t)
+#pragma unroll
+                                for (int k = 0; k < C::KSTEPS; ++k)
+                                    if (!(p.dbg & 2)) umma_f16_pair(d_item + t * 2 * COUT,
+                                             umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_hi + shift + t * 8 * C::ROWB + k * 32),
+                                             umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_pair,
+                                             (cc | tap | k) != 0 ? 1u : 0u);
+#pragma unroll
+                            for (int t = 0; t < C::NT; ++t)
+#pragma unroll
+                                for (int k = 0; k < C::KSTEPS; ++k)
+                                    if (!(p.dbg & 2)) umma_f16_pair(d_item + t * 2 * COUT,
+                                             umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_lo + shift + t * 8 * C::ROWB + k * 32),
+                                             umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_pair, 1u);
+                            umma_commit_pair(&b_empty[sb]);
                         }
                     }
-                    umma_commit(&a_empty[sa]);
+                    if (C::PAIR) umma_commit_pair(&a_empty[sa]);
+                    else umma_commit(&a_empty[sa]);
                 }
-                umma_commit(&tfull_bar[buf]);
+                if (C::PAIR) umma_commit_pair(&tfull_bar[buf]);
+                else umma_commit(&tfull_bar[buf]);
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -616,7 +718,10 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            if (lane == 0) {
+                if (C::PAIR) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[buf]), 0));
+                else mbar_arrive(&tempty_bar[buf]);
+            }
         }
         flush();
         if (lane == 0) bulk_wait_all();  // the staging buffers must outlive the TMA reads; stores complete before exit
@@ -833,7 +938,12 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 if (!(p.dbg & 1)) consume(cur, bc, stage_u32);
                 if (cur.b == NBATCH - 1) {
                     fence_proxy_async();
-                    mbar_arrive(&a_full[ait % C::A_STAGES]);
+                    if (C::PAIR) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&a_full[ait % C::A_STAGES]), 0));
+                    } else {
+                        mbar_arrive(&a_full[ait % C::A_STAGES]);
+                    }
                     ++ait;
                 }
                 advance(cur);
@@ -848,8 +958,12 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     }
     tc_fence_before();
     __syncthreads();
-    if (C::CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
-    if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (C::PAIR) {
+        cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still signal it or run MMAs on it
+        if (warp == 2) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    } else {
+        if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
 }
 
 // Plane statistics of conv0's output WITHOUT running conv0 (uint8 patterns).  conv0 has one input channel, so for
