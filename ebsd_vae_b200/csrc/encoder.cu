@@ -450,7 +450,7 @@ FusedWorkspace carve_fused(void *workspace, size_t chunk, size_t sub) {
 int fused_weight_box_rows(int layer) {
     const int cin = kPlan[layer].cin, cout = kPlan[layer].cout, kc = cin < 64 ? cin : 64;
     const bool resident = 9 * (cin / kc) * 2 * cout * kc * 2 <= 80 * 1024;
-    return resident || !EBSD_PAIR ? 2 * cout : cout;  // CTA pair: each CTA holds half of the stacked rows
+    return resident || !EBSD_PAIR ? 2 * cout : cout / 2;  // CTA pair: boxes of COUT/2 rows (FusedCfg::B_BOX_ROWS)
 }
 
 // fp32 [nimg,Wo,Wo,COUT] output as a 4-D tensor (c, x, y, n); box = (32 channels, bx, by, bn), 128B-swizzled in smem

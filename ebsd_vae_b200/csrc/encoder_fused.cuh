@@ -29,13 +29,12 @@ namespace ebsd {
 
 enum FusedSrc { SRC_U8 = 0, SRC_F32 = 1, SRC_RAW = 2 };
 
-// 1 = the blocks whose weights are streamed run as CTA pairs (tcgen05 cta_group::2, four-term product).  Correct
-// (the per-block parity tests pass in both modes) but MEASURED SLOWER on B200: under tensor load the chip is
-// power-limited (~1.4-1.7 GHz), the single-CTA three-term blocks already run at ~80 % of their clock-adjusted MMA
-// floor, and the fourth term costs 33 % more tensor work than the halved weight traffic saves
-// (profiles/README.md).  Kept as a build option: make EXTRA=-DEBSD_PAIR=1.
+// 1 = the blocks whose weights are streamed run as CTA pairs (tcgen05 cta_group::2, see FusedCfg::PAIR); measured
+// +4 % on the whole encoder against single CTAs (profiles/README.md).  A four-term variant of the pair (one B region,
+// N = 2*COUT for both planes) was tried first and lost: under tensor load the chip is power-limited and the extra
+// term costs more than the halved weight traffic saves.  0 = single CTAs (make EXTRA=-DEBSD_PAIR=0).
 #ifndef EBSD_PAIR
-#define EBSD_PAIR 0
+#define EBSD_PAIR 1
 #endif
 
 template <int CIN_, int COUT_, int W_, int SRC_, bool POOL_>
@@ -62,12 +61,16 @@ struct FusedCfg {
     // Streamed weights (the 64->64 ... 128->128 blocks) make the L2 -> SM weight traffic the limiter: one [w_hi; w_lo]
     // tile feeds only 128 output positions.  Those blocks therefore run as CTA PAIRS (tcgen05 cta_group::2, M = 256):
     // each CTA builds the window of its own work item and holds HALF of every weight tile (CTA 0 the w_hi rows, CTA 1
-    // the w_lo rows), so the weight bytes per SM halve and the ring is twice as deep.  Both planes use the same B
-    // operand (N = 2*COUT), i.e. the full four-term product a_hi*w_hi + a_hi*w_lo + a_lo*w_hi + a_lo*w_lo.
+    // the w_lo rows, plus half of w_hi for the lo plane): 25 % fewer weight bytes per SM, and the B operand reads of
+    // the tensor core halve, which matters because the single-CTA blocks are shared-memory-bandwidth bound.
     static constexpr bool PAIR = !RESIDENT_B && EBSD_PAIR;
     static constexpr int CL = PAIR ? 2 : 1;                  // cluster size
-    static constexpr int B_CTA = B_TILE / CL;                // weight bytes one CTA holds per (tap, K chunk)
-    static constexpr int B_CTA_ROWS = 2 * COUT / CL;
+    // PAIR: per (tap, K chunk) a CTA holds X = its half of [w_hi; w_lo] (COUT rows: rank 0 w_hi, rank 1 w_lo) for the
+    // hi-plane MMA (N = 2*COUT) and Y = its half of w_hi (COUT/2 rows) for the lo-plane MMA (N = COUT)
+    static constexpr int B_X = PAIR ? COUT * ROWB : B_TILE;
+    static constexpr int B_Y = PAIR ? (COUT / 2) * ROWB : 0;
+    static constexpr int B_CTA = B_X + B_Y;                  // weight bytes one CTA holds per (tap, K chunk)
+    static constexpr int B_BOX_ROWS = PAIR ? COUT / 2 : 2 * COUT;  // rows of one weight TMA box
     static constexpr int A_STAGES = 2;
     // output staging for the TMA stores: per epilogue warp one [32 or 8 rows][128 B] box, 128B-swizzled
     static constexpr int WSTG = POOL ? 1024 : 4096;
@@ -375,12 +378,15 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                                 tma_load_2d(smem_b + sb * C::B_TILE, &map_w, 0, (tap * C::NCHUNK + cc) * 2 * COUT,
                                             &b_full[sb]);
                             } else {
-                                // this CTA's half of the tile (rank 0: w_hi rows, rank 1: w_lo rows); the leader's
-                                // barrier collects the bytes of both halves
-                                if (cta_rank == 0) mbar_expect_tx(&b_full[sb], C::B_TILE);
-                                tma_load_2d_pair(smem_u32(smem_b + sb * C::B_CTA), &map_w, 0,
-                                                 (tap * C::NCHUNK + cc) * 2 * COUT + (int)cta_rank * C::B_CTA_ROWS,
-                                                 map_to_cta(smem_u32(&b_full[sb]), 0));
+                                // X: this CTA's half of [w_hi; w_lo] (two boxes of COUT/2 rows), Y: its half of w_hi;
+                                // the leader's barrier collects the bytes of both CTAs
+                                if (cta_rank == 0) mbar_expect_tx(&b_full[sb], 2 * C::B_CTA);
+                                const int row0 = (tap * C::NCHUNK + cc) * 2 * COUT;
+                                const uint32_t dst = smem_u32(smem_b + sb * C::B_CTA);
+                                const uint32_t lbar = map_to_cta(smem_u32(&b_full[sb]), 0);
+                                tma_load_2d_pair(dst, &map_w, 0, row0 + (int)cta_rank * COUT, lbar);
+                                tma_load_2d_pair(dst + C::B_X / 2, &map_w, 0, row0 + (int)cta_rank * COUT + COUT / 2, lbar);
+                                tma_load_2d_pair(dst + C::B_X, &map_w, 0, row0 + (int)cta_rank * (COUT / 2), lbar);
                             }
                         }
                 }
@@ -466,9 +472,10 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                             umma_commit(&b_empty[sb]);
                         }
                     } else {
-                        // CTA pair: M = 256 (this CTA's window rows + the peer's), N = 2*COUT with half of the weight
-                        // rows in each CTA; the hi and the lo plane use the same B operand (four-term product)
+                        // CTA pair: M = 256 (this CTA's window rows + the peer's); hi plane: N = 2*COUT, B = X (w_hi rows in
+                        // the leader, w_lo rows in the peer); lo plane: N = COUT, B = Y (w_hi split between the CTAs)
                         constexpr uint32_t idesc_pair = umma_idesc_f16_m256(2 * COUT);
+                        constexpr uint32_t idesc_pair_lo = umma_idesc_f16_m256(COUT);
 #pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap, ++bit) {
                             const int dy = tap / 3, dx = tap - dy * 3;
@@ -491,7 +498,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                                 for (int k = 0; k < C::KSTEPS; ++k)
                                     if (!(p.dbg & 2)) umma_f16_pair(d_item + t * 2 * COUT,
                                              umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_lo + shift + t * 8 * C::ROWB + k * 32),
-                                             umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_pair, 1u);
+                                             umma_smem_desc_g<C::ROWB, 8>(b_w + C::B_X + k * 32), idesc_pair_lo, 1u);
                             umma_commit_pair(&b_empty[sb]);
                         }
                     }
