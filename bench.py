@@ -44,6 +44,58 @@ TOP_N = 10
 THRESHOLD = 3.0
 MIN_REQUIRED = 5          # exercises the symmetry + mean path (the reference default 18 > top_n always fails)
 F_ENC = 1_406_271_488     # algorithmic FLOP per pattern: ten convolutions + mu/logvar heads
+# (Cin, Cout, H=W, pooled) of the nine tensor-core blocks; block 1 also runs conv0 (1 -> 32) in its producers
+BLOCKS = {1: (32, 32, 128, 1), 2: (32, 64, 64, 0), 3: (64, 64, 64, 1), 4: (64, 128, 32, 0), 5: (128, 128, 32, 1),
+          6: (128, 128, 16, 0), 7: (128, 128, 16, 1), 8: (128, 128, 8, 0), 9: (128, 128, 8, 1)}
+# DRAM bytes per pattern of the whole encoder chain (dram__bytes_read.sum + dram__bytes_write.sum summed over the
+# chain's kernels, ncu pass recorded in profiles/r01_encoder_dram_tensor_summary.txt: 6595 MB per 1184 patterns)
+ENCODER_DRAM_BYTES_PER_PATTERN = 5_570_100
+
+
+def block_flop(layer: int) -> int:
+    cin, cout, hw, _ = BLOCKS[layer]
+    f = 2 * 9 * cin * cout * hw * hw
+    if layer == 1:
+        f += 2 * 9 * 1 * 32 * 128 * 128   # conv0, computed by block 1's producer warps
+    return f
+
+
+def time_blocks(torch, engine, lib, n_img: int = 1184):
+    """Live CUDA-event timing of every fused block on its own (test hook of the C ABI): algorithmic TFLOP/s each."""
+    from ebsd_vae_b200 import _native
+
+    out = {}
+    st = torch.cuda.current_stream().cuda_stream
+    for layer, (cin, cout, hw, pool) in BLOCKS.items():
+        if layer == 1:
+            src = torch.randint(0, 256, (n_img, 128, 128), dtype=torch.uint8, device="cuda")
+            src_sums = torch.zeros((n_img, 32, 2), dtype=torch.float64, device="cuda")
+        else:
+            src = torch.randn((n_img, hw, hw, cin), device="cuda")
+            x = src.double()
+            src_sums = torch.stack([x.sum(dim=(1, 2)), (x * x).sum(dim=(1, 2))], dim=2).contiguous()
+            del x
+        ho = hw // 2 if pool else hw
+        raw = torch.empty((n_img, ho, ho, cout), device="cuda")
+        sums = torch.zeros((n_img, cout, 2), dtype=torch.float64, device="cuda")
+
+        def run():
+            _native.check(lib.ebsd_debug_fused_layer(engine._handle, layer, 0, src.data_ptr(), src_sums.data_ptr(),
+                                                     hw * hw, n_img, raw.data_ptr(), sums.data_ptr(), st), "block")
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 3 * 1e3
+        out[f"block{layer}"] = {"us_per_%d_patterns" % n_img: round(us, 1),
+                                "tflops": round(n_img * block_flop(layer) / (us * 1e-6) / 1e12, 1)}
+        del src, src_sums, raw, sums
+    return out
 
 
 def load_peaks():
@@ -357,9 +409,13 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
         "kernel": "ebsd_encoder_forward: conv/InstanceNorm/pool chain + heads (dominant, %.1f %% of the step)"
                   % (100.0 * enc_ms / ms_step),
         "bound": "tensor", "achieved": enc_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": enc_tflops / peak_tf,
-        "traffic": None,
+        "traffic": N_QUERY_PER_GPU * ENCODER_DRAM_BYTES_PER_PATTERN,
+        "traffic_note": "DRAM bytes per step of the encoder chain, from the ncu pass in profiles/ (per pattern x patterns)",
         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
         "algorithmic_flop_per_pattern": F_ENC,
+        "precision_note": "fp32-accurate convolution = three fp16 tensor-core products per algorithmic MAC, so the "
+                          "algorithmic ceiling is 1/3 of the tensor peak (frac <= 0.333)",
+        "blocks": time_blocks(torch, engine, lib) if rank == 0 else None,
     }
     stages = {
         "encoder_ms": enc_ms, "topk_ms": topk_ms, "consensus_ms": cons_ms,

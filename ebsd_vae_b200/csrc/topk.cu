@@ -17,6 +17,7 @@
 //   * ties: dot descending, then row index ascending -- rows arrive in ascending order and tau only lets
 //     strictly larger dots through once the list is full, which is exactly that rule.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -94,7 +95,7 @@ struct Smem {
 };
 
 template <int TQ>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, TQ <= 4 ? 2 : 1)
 topk_kernel(const __grid_constant__ CUtensorMap dict_map, const TopkParams p) {
     using S = Smem<TQ>;
     constexpr int QT = S::QT;
@@ -372,9 +373,22 @@ struct TopkPlan {
     int tiles_per_split;
 };
 
+// queries per thread of the batched kernel: 4 (two CTAs of 8 warps per SM; default -- 16 resident warps hide the
+// shared-memory and FMA latencies, measured 1.2-2.3x faster than one CTA of TQ = 8, profiles/README.md) or 8 (one CTA
+// per SM, 64 accumulators per thread).  EBSD_TOPK_TQ=8 selects the latter for A/B timing.
+static int topk_tq() {
+    static int tq = 0;
+    if (tq == 0) {
+        const char *e = getenv("EBSD_TOPK_TQ");
+        tq = (e && atoi(e) == 8) ? 8 : 4;
+    }
+    return tq;
+}
+
 static TopkPlan make_plan(long long N, long long Q, int sms) {
     TopkPlan pl;
-    pl.tq = Q <= 16 ? 1 : 8;
+    pl.tq = Q <= 16 ? 1 : topk_tq();
+    sms *= pl.tq <= 4 ? 2 : 1;  // CTA slots: the TQ <= 4 kernels run two CTAs per SM
     pl.qt = kWarps * 2 * pl.tq;
     pl.n_qtiles = (int)((Q + pl.qt - 1) / pl.qt);
     const long long total_tiles = (N + kTileRows - 1) / kTileRows;
@@ -414,7 +428,8 @@ static int launch_topk(const CUtensorMap &map, const TopkParams &p, int sms, cud
         configured = true;
     }
     const int n_items = p.n_qtiles * p.n_splits;
-    const int grid = n_items < sms ? n_items : sms;
+    const int slots = sms * (TQ <= 4 ? 2 : 1);  // resident CTAs
+    const int grid = n_items < slots ? n_items : slots;
     topk_kernel<TQ><<<grid, kThreads, S::alloc, st>>>(map, p);
     EBSD_LAUNCH_CHECK();
     return EBSD_OK;
@@ -507,7 +522,8 @@ int ebsd_topk(const float *dict, int64_t N, int64_t index_base, const float *que
     p.out_dot = out_dot;
     p.out_idx = (long long *)out_idx;
     p.out_dist = out_dist;
-    rc = pl.tq == 8 ? launch_topk<8>(map, p, sms, st) : launch_topk<1>(map, p, sms, st);
+    rc = pl.tq == 8 ? launch_topk<8>(map, p, sms, st)
+                    : (pl.tq == 4 ? launch_topk<4>(map, p, sms, st) : launch_topk<1>(map, p, sms, st));
     if (rc) return rc;
     if (pl.n_splits > 1) {
         const int wpb = 8;
