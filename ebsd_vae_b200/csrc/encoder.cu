@@ -412,13 +412,23 @@ int forward_chunk_mma2(const ebsd_encoder *enc, const void *pin, int dtype, int 
 // small enough that a block's output is still in the 126 MB L2 when the next block reads it and is overwritten by
 // the next sub-chunk before it is ever written back; blocks 4..9 (<= 0.5 MB per image) run over the whole chunk so
 // that even the 8x8 blocks fill all SMs.
-constexpr int kChunkFused = 1184;                      // images per pass (8 per SM): long launches amortise pipeline fill
-constexpr int kSubFused = 1184;                        // images per early sub-chunk (blocks 0..3); measured: L2 residency
+constexpr int kChunkFused = 1480;                      // most images per pass (10 per SM): long launches amortise pipeline fill
+constexpr int kSubFused = 1480;                        // images per early sub-chunk (blocks 0..3); measured: L2 residency
                                                        // gains less than the extra launches cost, so sub = chunk
 constexpr size_t kFusedRaw1Floats = 64ull * 64 * 32;   // per image: pooled output of conv1
 constexpr size_t kFusedRaw2Floats = 64ull * 64 * 64;   // per image: output of conv2
 constexpr size_t kFusedRaw3Floats = 32ull * 32 * 64;   // per image: pooled output of conv3 (largest tenant of late buffer 0)
 constexpr size_t kFusedRaw4Floats = 32ull * 32 * 128;  // per image: output of conv4 (largest tenant of late buffer 1)
+
+// Images per pass for a batch of B: as few passes as the cap allows, all of (nearly) equal size -- a short last
+// pass would run the same 12 launches with a fraction of the work.
+size_t fused_chunk_for(int64_t B, int cap) {
+    if (B <= cap) return (size_t)B;
+    const int64_t passes = (B + cap - 1) / cap;
+    int64_t c = (B + passes - 1) / passes;
+    c += c & 1;  // the 8x8 blocks take images in pairs
+    return (size_t)(c < cap ? c : cap);
+}
 
 struct FusedWorkspace {
     float *raw1, *raw2;    // sub-chunk level
@@ -448,9 +458,8 @@ FusedWorkspace carve_fused(void *workspace, size_t chunk, size_t sub) {
 // rows of the packed weights one CTA fetches per (tap, K chunk): the whole [w_hi; w_lo] tile, or its 1/CL slice
 // when the block runs as a CTA pair (FusedCfg::RESIDENT_B / PAIR)
 int fused_weight_box_rows(int layer) {
-    const int cin = kPlan[layer].cin, cout = kPlan[layer].cout, kc = cin < 64 ? cin : 64;
-    const bool resident = 9 * (cin / kc) * 2 * cout * kc * 2 <= 80 * 1024;
-    return resident || !EBSD_PAIR ? 2 * cout : cout / 2;  // CTA pair: boxes of COUT/2 rows (FusedCfg::B_BOX_ROWS)
+    const int cout = kPlan[layer].cout;
+    return (EBSD_PAIR && kPlan[layer].cin >= 64) ? cout / 2 : 2 * cout;  // FusedCfg::PAIR, B_BOX_ROWS
 }
 
 // fp32 [nimg,Wo,Wo,COUT] output as a 4-D tensor (c, x, y, n); box = (32 channels, bx, by, bn), 128B-swizzled in smem
@@ -722,7 +731,7 @@ size_t ebsd_encoder_workspace_bytes(const ebsd_encoder *enc, int64_t B) {
     const int chunk_cap = (enc && enc->use_mma) ? kChunkMma : kChunk;
     const size_t nimg = (size_t)(B < chunk_cap ? B : chunk_cap);
     if (enc && enc->use_mma == 3) {
-        const size_t c = (size_t)(B < enc->chunk ? B : enc->chunk);
+        const size_t c = fused_chunk_for(B, enc->chunk);
         return carve_fused(nullptr, c, (size_t)enc->sub).bytes + 1024;
     }
     if (enc && enc->use_mma == 2) return carve_mma2(nullptr, nimg).bytes + 1024;
@@ -754,7 +763,7 @@ int ebsd_encoder_forward(ebsd_encoder *enc, const void *patterns, int dtype, int
 
     const size_t px_bytes = dtype == EBSD_PATTERN_U8 ? 1 : 4;
     if (enc->use_mma == 3) {
-        const size_t fchunk = (size_t)(B < enc->chunk ? B : enc->chunk);
+        const size_t fchunk = fused_chunk_for(B, enc->chunk);
         const FusedWorkspace wf = carve_fused(workspace, fchunk, (size_t)enc->sub);
         for (int64_t b0 = 0; b0 < B; b0 += (int64_t)fchunk) {
             const int nimg = (int)((B - b0) < (int64_t)fchunk ? (B - b0) : (int64_t)fchunk);

@@ -43,33 +43,36 @@ struct FusedCfg {
     static constexpr bool POOL = POOL_;                      // 2x2 max-pool of the raw output in the epilogue
     static constexpr bool FIRST = SRC_ != SRC_RAW;           // conv0 is computed by the producers (CIN = 32, W = 128)
     static constexpr int NI = W == 8 ? 2 : 1;                // images interleaved in one window row
-    static constexpr int NT = W >= 128 ? 4 : (W >= 64 ? 2 : 1);  // tiles per work item
-    static constexpr int TR = 16 / NI;                       // image rows per tile
-    static constexpr int WIN_H = TR + 2;
-    static constexpr int PITCH = NI == 1 ? 8 * NT + 2 : 10 * NI;
-    static constexpr int GSTRIDE = NI == 1 ? PITCH : 10;     // window rows between consecutive 8-row groups
-    static constexpr int WIN_POS = WIN_H * PITCH;
+    // CTA pairs (tcgen05 cta_group::2, see below) for the blocks with >= 64 input channels.  The two 32-channel blocks
+    // were measured slower as pairs (1490 -> 1568 and 543 -> 627 us per 1184 patterns): their MMA streams are short and
+    // the lock step of two producer groups costs more than the halved B reads save.
+    static constexpr bool PAIR = EBSD_PAIR != 0 && CIN >= 64;
     static constexpr int KC = CIN < 64 ? CIN : 64;
     static constexpr int ROWB = KC * 2;
-    static constexpr int SWMASK = ROWB == 128 ? 7 : 3;
     static constexpr int NCHUNK = CIN / KC;
-    static constexpr int KSTEPS = KC / 16;
-    static constexpr int A_PLANE = (WIN_POS * ROWB + 1023) / 1024 * 1024;
-    static constexpr int A_STAGE = 2 * A_PLANE;              // hi + lo
     static constexpr int B_TILE = 2 * COUT * ROWB;           // [w_hi; w_lo] of one (tap, K chunk)
-    static constexpr bool RESIDENT_B = 9 * NCHUNK * B_TILE <= 80 * 1024;
-    // Streamed weights (the 64->64 ... 128->128 blocks) make the L2 -> SM weight traffic the limiter: one [w_hi; w_lo]
-    // tile feeds only 128 output positions.  Those blocks therefore run as CTA PAIRS (tcgen05 cta_group::2, M = 256):
-    // each CTA builds the window of its own work item and holds HALF of every weight tile (CTA 0 the w_hi rows, CTA 1
-    // the w_lo rows, plus half of w_hi for the lo plane): 25 % fewer weight bytes per SM, and the B operand reads of
-    // the tensor core halve, which matters because the single-CTA blocks are shared-memory-bandwidth bound.
-    static constexpr bool PAIR = !RESIDENT_B && EBSD_PAIR;
-    static constexpr int CL = PAIR ? 2 : 1;                  // cluster size
     // PAIR: per (tap, K chunk) a CTA holds X = its half of [w_hi; w_lo] (COUT rows: rank 0 w_hi, rank 1 w_lo) for the
     // hi-plane MMA (N = 2*COUT) and Y = its half of w_hi (COUT/2 rows) for the lo-plane MMA (N = COUT)
     static constexpr int B_X = PAIR ? COUT * ROWB : B_TILE;
     static constexpr int B_Y = PAIR ? (COUT / 2) * ROWB : 0;
     static constexpr int B_CTA = B_X + B_Y;                  // weight bytes one CTA holds per (tap, K chunk)
+    // all nine taps stay in shared memory when they fit next to two windows: the 32-channel blocks always, the
+    // 64 -> 64 block only as a pair (108 KB per CTA) and with one tile per window
+    static constexpr bool RESIDENT_B = 9 * NCHUNK * B_CTA <= (PAIR ? 112 : 80) * 1024;
+    static constexpr int NT = W >= 128 ? 4 : (W >= 64 ? ((RESIDENT_B && CIN == 64) ? 1 : 2) : 1);  // tiles per work item
+    static constexpr int TR = 16 / NI;                       // image rows per tile
+    static constexpr int WIN_H = TR + 2;
+    static constexpr int PITCH = NI == 1 ? 8 * NT + 2 : 10 * NI;
+    static constexpr int GSTRIDE = NI == 1 ? PITCH : 10;     // window rows between consecutive 8-row groups
+    static constexpr int WIN_POS = WIN_H * PITCH;
+    static constexpr int SWMASK = ROWB == 128 ? 7 : 3;
+    static constexpr int KSTEPS = KC / 16;
+    static constexpr int A_PLANE = (WIN_POS * ROWB + 1023) / 1024 * 1024;
+    static constexpr int A_STAGE = 2 * A_PLANE;              // hi + lo
+    // CTA PAIRS (tcgen05 cta_group::2, M = 256): each CTA builds the window of its own work item and holds HALF of
+    // every weight tile; the leader issues one MMA stream for both.  25 % fewer weight bytes per SM and half the B
+    // operand reads of the tensor core, which matters because the single-CTA blocks are shared-memory-bandwidth bound.
+    static constexpr int CL = PAIR ? 2 : 1;                  // cluster size
     static constexpr int B_BOX_ROWS = PAIR ? COUT / 2 : 2 * COUT;  // rows of one weight TMA box
     static constexpr int A_STAGES = 2;
     // output staging for the TMA stores: per epilogue warp one [32 or 8 rows][128 B] box, 128B-swizzled
@@ -350,19 +353,32 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 }
                 tma_prefetch_l2_4d(&map_src, 0, x0, y0, n);
             };
-            for (int j = 0; j < PF; ++j) prefetch_item(item_begin + j);
-            if (C::RESIDENT_B) {
-                for (int kb = 0; kb < 9 * C::NCHUNK; ++kb) {
-                    mbar_expect_tx(&b_full[kb], C::B_TILE);
-                    tma_load_2d(smem_b + kb * C::B_TILE, &map_w, 0, kb * 2 * COUT, &b_full[kb]);
+            for (int j = 0; j < PF + (C::RESIDENT_B ? C::A_STAGES : 0); ++j) prefetch_item(item_begin + j);
+            // one weight tile: a whole [w_hi; w_lo] box, or (PAIR) this CTA's X and Y parts in boxes of COUT/2 rows,
+            // with the bytes of both CTAs credited to the leader's barrier
+            auto load_weights = [&](uint8_t *dst_ptr, int kb, uint64_t *bar) {
+                if (!C::PAIR) {
+                    mbar_expect_tx(bar, C::B_TILE);
+                    tma_load_2d(dst_ptr, &map_w, 0, kb * 2 * COUT, bar);
+                } else {
+                    if (cta_rank == 0) mbar_expect_tx(bar, 2 * C::B_CTA);
+                    const int row0 = kb * 2 * COUT;
+                    const uint32_t dst = smem_u32(dst_ptr);
+                    const uint32_t lbar = map_to_cta(smem_u32(bar), 0);
+                    tma_load_2d_pair(dst, &map_w, 0, row0 + (int)cta_rank * COUT, lbar);
+                    tma_load_2d_pair(dst + C::B_X / 2, &map_w, 0, row0 + (int)cta_rank * COUT + COUT / 2, lbar);
+                    tma_load_2d_pair(dst + C::B_X, &map_w, 0, row0 + (int)cta_rank * (COUT / 2), lbar);
                 }
+            };
+            if (C::RESIDENT_B) {
+                for (int kb = 0; kb < 9 * C::NCHUNK; ++kb) load_weights(smem_b + kb * C::B_CTA, kb, &b_full[kb]);
                 if (!C::FIRST) {
-                    // pace the prefetches with the windows becoming ready (a_full is only observed here)
+                    // pace the prefetches with the windows being consumed (a_empty arrives in both CTAs of a pair)
                     unsigned ait = 0;
                     for (int item = item_begin; item < item_end; ++item)
                         for (int cc = 0; cc < C::NCHUNK; ++cc, ++ait) {
-                            mbar_wait_bounded(&a_full[ait % C::A_STAGES], (ait / C::A_STAGES) & 1u);
-                            if (cc == 0) prefetch_item(item + PF);
+                            mbar_wait_bounded(&a_empty[ait % C::A_STAGES], (ait / C::A_STAGES) & 1u);
+                            if (cc == 0) prefetch_item(item + PF + C::A_STAGES);
                         }
                 }
             } else {
@@ -373,21 +389,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                         for (int tap = 0; tap < 9; ++tap, ++bit) {
                             const int sb = bit % C::B_STAGES;
                             mbar_wait_bounded(&b_empty[sb], ((bit / C::B_STAGES) & 1u) ^ 1u);
-                            if (!C::PAIR) {
-                                mbar_expect_tx(&b_full[sb], C::B_TILE);
-                                tma_load_2d(smem_b + sb * C::B_TILE, &map_w, 0, (tap * C::NCHUNK + cc) * 2 * COUT,
-                                            &b_full[sb]);
-                            } else {
-                                // X: this CTA's half of [w_hi; w_lo] (two boxes of COUT/2 rows), Y: its half of w_hi;
-                                // the leader's barrier collects the bytes of both CTAs
-                                if (cta_rank == 0) mbar_expect_tx(&b_full[sb], 2 * C::B_CTA);
-                                const int row0 = (tap * C::NCHUNK + cc) * 2 * COUT;
-                                const uint32_t dst = smem_u32(smem_b + sb * C::B_CTA);
-                                const uint32_t lbar = map_to_cta(smem_u32(&b_full[sb]), 0);
-                                tma_load_2d_pair(dst, &map_w, 0, row0 + (int)cta_rank * COUT, lbar);
-                                tma_load_2d_pair(dst + C::B_X / 2, &map_w, 0, row0 + (int)cta_rank * COUT + COUT / 2, lbar);
-                                tma_load_2d_pair(dst + C::B_X, &map_w, 0, row0 + (int)cta_rank * (COUT / 2), lbar);
-                            }
+                            load_weights(smem_b + sb * C::B_CTA, tap * C::NCHUNK + cc, &b_full[sb]);
                         }
                 }
             }
@@ -395,118 +397,82 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     } else if (warp == 1) {
         // ===================== MMA issuer (PAIR: the leader CTA issues for both)
         if (cta_rank == 0 && elect_one_sync()) {
-            constexpr uint32_t idesc_n2 = umma_idesc_f16(2 * COUT);
-            constexpr uint32_t idesc_n1 = umma_idesc_f16(COUT);
+            // hi plane: N = 2*COUT against [w_hi; w_lo]; lo plane: N = COUT against w_hi.  PAIR: M = 256 (this CTA's
+            // window rows + the peer's) with the B rows split between the two CTAs (X / Y regions of the stage)
+            constexpr uint32_t idesc_hi = C::PAIR ? umma_idesc_f16_m256(2 * COUT) : umma_idesc_f16(2 * COUT);
+            constexpr uint32_t idesc_lo = C::PAIR ? umma_idesc_f16_m256(COUT) : umma_idesc_f16(COUT);
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+                if (p.dbg & 2) return;
+                if (C::PAIR) umma_f16_pair(d, da, db, idesc, acc);
+                else umma_f16(d, da, db, idesc, acc);
+            };
+            auto commit = [&](uint64_t *bar) {
+                if (C::PAIR) umma_commit_pair(bar);
+                else umma_commit(bar);
+            };
+            auto wait = [&](uint64_t *bar, uint32_t parity) {
+                if (C::PAIR) mbar_wait_cluster(bar, parity);
+                else mbar_wait_bounded(bar, parity);
+            };
+            // all MMAs of one plane for one tap: NT tiles x KSTEPS
+            auto tap_mmas = [&](uint32_t d_item, uint32_t win, uint32_t b_w, uint32_t idesc, bool first) {
+#pragma unroll
+                for (int t = 0; t < C::NT; ++t)
+#pragma unroll
+                    for (int k = 0; k < C::KSTEPS; ++k)
+                        mma(d_item + t * 2 * COUT, umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win + t * 8 * C::ROWB + k * 32),
+                            umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc, (first && k == 0) ? 0u : 1u);
+            };
             if (C::RESIDENT_B) {
-                for (int kb = 0; kb < 9 * C::NCHUNK; ++kb) mbar_wait_bounded(&b_full[kb], 0);
+                for (int kb = 0; kb < 9 * C::NCHUNK; ++kb) wait(&b_full[kb], 0);
                 tc_fence_after();
             }
             unsigned ait = 0, bit = 0;
             int j = 0;
             for (int item = item_begin; item < item_end; ++item, ++j) {
                 const int buf = j & 1;
-                if (C::PAIR) mbar_wait_cluster(&tempty_bar[buf], (((unsigned)j >> 1) & 1u) ^ 1u);
-                else mbar_wait_bounded(&tempty_bar[buf], (((unsigned)j >> 1) & 1u) ^ 1u);
+                wait(&tempty_bar[buf], (((unsigned)j >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_item = tmem_base + (uint32_t)(buf * C::ACC_COLS);
                 for (int cc = 0; cc < C::NCHUNK; ++cc, ++ait) {
                     const int sa = ait % C::A_STAGES;
-                    if (C::PAIR) mbar_wait_cluster(&a_full[sa], (ait / C::A_STAGES) & 1u);
-                    else mbar_wait_bounded(&a_full[sa], (ait / C::A_STAGES) & 1u);
+                    wait(&a_full[sa], (ait / C::A_STAGES) & 1u);
                     tc_fence_after();
                     const uint32_t win_hi = smem_u32(smem + sa * C::A_STAGE);
                     const uint32_t win_lo = win_hi + C::A_PLANE;
                     if (C::RESIDENT_B) {
-                        // all hi-plane MMAs (N = 2*COUT), then all lo-plane MMAs (N = COUT): two descriptor switches
+                        // all hi-plane MMAs, then all lo-plane MMAs: two instruction-descriptor switches per window
 #pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap) {
                             const int dy = tap / 3, dx = tap - dy * 3;
                             const uint32_t shift = (uint32_t)((dy * C::PITCH + dx) * C::ROWB);
-                            const uint32_t b_w = smem_u32(smem_b + (tap * C::NCHUNK + cc) * C::B_TILE);
-#pragma unroll
-                            for (int t = 0; t < C::NT; ++t)
-#pragma unroll
-                                for (int k = 0; k < C::KSTEPS; ++k)
-                                    if (!(p.dbg & 2)) umma_f16(d_item + t * 2 * COUT,
-                                             umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_hi + shift + t * 8 * C::ROWB + k * 32),
-                                             umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_n2,
-                                             (cc | tap | k) != 0 ? 1u : 0u);
+                            const uint32_t b_w = smem_u32(smem_b + (tap * C::NCHUNK + cc) * C::B_CTA);
+                            tap_mmas(d_item, win_hi + shift, b_w, idesc_hi, (cc | tap) == 0);
                         }
 #pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap) {
                             const int dy = tap / 3, dx = tap - dy * 3;
                             const uint32_t shift = (uint32_t)((dy * C::PITCH + dx) * C::ROWB);
-                            const uint32_t b_w = smem_u32(smem_b + (tap * C::NCHUNK + cc) * C::B_TILE);
-#pragma unroll
-                            for (int t = 0; t < C::NT; ++t)
-#pragma unroll
-                                for (int k = 0; k < C::KSTEPS; ++k)
-                                    if (!(p.dbg & 2)) umma_f16(d_item + t * 2 * COUT,
-                                             umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_lo + shift + t * 8 * C::ROWB + k * 32),
-                                             umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_n1, 1u);
-                        }
-                    } else if (!C::PAIR) {
-#pragma unroll 1
-                        for (int tap = 0; tap < 9; ++tap, ++bit) {
-                            const int dy = tap / 3, dx = tap - dy * 3;
-                            const uint32_t shift = (uint32_t)((dy * C::PITCH + dx) * C::ROWB);
-                            const int sb = bit % C::B_STAGES;
-                            mbar_wait_bounded(&b_full[sb], (bit / C::B_STAGES) & 1u);
-                            tc_fence_after();
-                            const uint32_t b_w = smem_u32(smem_b + sb * C::B_TILE);
-#pragma unroll
-                            for (int t = 0; t < C::NT; ++t)
-#pragma unroll
-                                for (int k = 0; k < C::KSTEPS; ++k)
-                                    if (!(p.dbg & 2)) umma_f16(d_item + t * 2 * COUT,
-                                             umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_hi + shift + t * 8 * C::ROWB + k * 32),
-                                             umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_n2,
-                                             (cc | tap | k) != 0 ? 1u : 0u);
-#pragma unroll
-                            for (int t = 0; t < C::NT; ++t)
-#pragma unroll
-                                for (int k = 0; k < C::KSTEPS; ++k)
-                                    if (!(p.dbg & 2)) umma_f16(d_item + t * 2 * COUT,
-                                             umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_lo + shift + t * 8 * C::ROWB + k * 32),
-                                             umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_n1, 1u);
-                            umma_commit(&b_empty[sb]);
+                            const uint32_t b_w = smem_u32(smem_b + (tap * C::NCHUNK + cc) * C::B_CTA);
+                            tap_mmas(d_item, win_lo + shift, b_w + (C::PAIR ? C::B_X : 0), idesc_lo, false);
                         }
                     } else {
-                        // CTA pair: M = 256 (this CTA's window rows + the peer's); hi plane: N = 2*COUT, B = X (w_hi rows in
-                        // the leader, w_lo rows in the peer); lo plane: N = COUT, B = Y (w_hi split between the CTAs)
-                        constexpr uint32_t idesc_pair = umma_idesc_f16_m256(2 * COUT);
-                        constexpr uint32_t idesc_pair_lo = umma_idesc_f16_m256(COUT);
 #pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap, ++bit) {
                             const int dy = tap / 3, dx = tap - dy * 3;
                             const uint32_t shift = (uint32_t)((dy * C::PITCH + dx) * C::ROWB);
                             const int sb = bit % C::B_STAGES;
-                            mbar_wait_bounded(&b_full[sb], (bit / C::B_STAGES) & 1u);
+                            wait(&b_full[sb], (bit / C::B_STAGES) & 1u);
                             tc_fence_after();
                             const uint32_t b_w = smem_u32(smem_b + sb * C::B_CTA);
-#pragma unroll
-                            for (int t = 0; t < C::NT; ++t)
-#pragma unroll
-                                for (int k = 0; k < C::KSTEPS; ++k)
-                                    if (!(p.dbg & 2)) umma_f16_pair(d_item + t * 2 * COUT,
-                                             umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_hi + shift + t * 8 * C::ROWB + k * 32),
-                                             umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc_pair,
-                                             (cc | tap | k) != 0 ? 1u : 0u);
-#pragma unroll
-                            for (int t = 0; t < C::NT; ++t)
-#pragma unroll
-                                for (int k = 0; k < C::KSTEPS; ++k)
-                                    if (!(p.dbg & 2)) umma_f16_pair(d_item + t * 2 * COUT,
-                                             umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win_lo + shift + t * 8 * C::ROWB + k * 32),
-                                             umma_smem_desc_g<C::ROWB, 8>(b_w + C::B_X + k * 32), idesc_pair_lo, 1u);
-                            umma_commit_pair(&b_empty[sb]);
+                            tap_mmas(d_item, win_hi + shift, b_w, idesc_hi, (cc | tap) == 0);
+                            tap_mmas(d_item, win_lo + shift, b_w + (C::PAIR ? C::B_X : 0), idesc_lo, false);
+                            commit(&b_empty[sb]);
                         }
                     }
-                    if (C::PAIR) umma_commit_pair(&a_empty[sa]);
-                    else umma_commit(&a_empty[sa]);
+                    commit(&a_empty[sa]);
                 }
-                if (C::PAIR) umma_commit_pair(&tfull_bar[buf]);
-                else umma_commit(&tfull_bar[buf]);
+                commit(&tfull_bar[buf]);
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -796,7 +762,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     const int py = idx / 36, px = idx - py * 36;
                     const int gy = y0 - 2 + py, gx = x0 - 2 + px;
                     uint32_t v = 0u;
-                    if (idx < 20 * 36 && gy >= 0 && gy < 128 && gx >= 0 && gx < 128) {
+                    if (idx < 20 * 36 && n < p.nimg && gy >= 0 && gy < 128 && gx >= 0 && gx < 128) {
                         const long long off = ((long long)n * 128 + gy) * 128 + gx;
                         if (SRC == SRC_U8) v = __ldg((const uint8_t *)p.src + off);
                         else v = __float_as_uint(__ldg((const float *)p.src + off));
@@ -852,7 +818,12 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     store_chunk<C>(stage_u32, pos, cg, hi, lo);
                 }
                 fence_proxy_async();
-                mbar_arrive(&a_full[sa]);
+                if (C::PAIR) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&a_full[sa]), 0));
+                } else {
+                    mbar_arrive(&a_full[sa]);
+                }
             }
         } else {
             // raw fp32 -> normalise -> LeakyReLU -> fp16 hi / lo.  One unit = 8 channels of one window position; the

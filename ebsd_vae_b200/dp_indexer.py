@@ -50,7 +50,7 @@ class DiffractionPatternIndexer:
     """Indexes diffraction patterns using the VAE encoder and the GPU latent dictionary."""
 
     #: patterns encoded per native call inside build_dictionary / encode_patterns_batch (host staging granularity)
-    ENCODE_CHUNK = 2368
+    ENCODE_CHUNK = 2960
 
     def __init__(self, model, db: LatentVectorDatabase | None = None, config: IndexerConfig | None = None) -> None:
         self.config = config if config is not None else IndexerConfig()
@@ -102,16 +102,20 @@ class DiffractionPatternIndexer:
         dev = torch.empty(t.shape, dtype=t.dtype, device=self.device)
         mu = torch.empty((b, self.config.latent_dim), dtype=torch.float32, device=self.device)
         self._copy_stream.wait_stream(compute)  # `dev` was allocated on the compute stream
+        # slices of (nearly) equal size, at most ENCODE_CHUNK patterns each
+        n_slices = (b + self.ENCODE_CHUNK - 1) // self.ENCODE_CHUNK
+        step = (b + n_slices - 1) // n_slices
+        step += step & 1
         events = []
         with torch.cuda.stream(self._copy_stream):
-            for a in range(0, b, self.ENCODE_CHUNK):
-                dev[a : a + self.ENCODE_CHUNK].copy_(t[a : a + self.ENCODE_CHUNK], non_blocking=True)
+            for a in range(0, b, step):
+                dev[a : a + step].copy_(t[a : a + step], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._copy_stream)
                 events.append(ev)
-        for i, a in enumerate(range(0, b, self.ENCODE_CHUNK)):
+        for i, a in enumerate(range(0, b, step)):
             compute.wait_event(events[i])
-            mu[a : a + self.ENCODE_CHUNK] = self.engine.encode(dev[a : a + self.ENCODE_CHUNK])
+            mu[a : a + step] = self.engine.encode(dev[a : a + step])
         return mu
 
     def _encode_u8_host(self, u8: np.ndarray) -> torch.Tensor:
