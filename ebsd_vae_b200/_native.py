@@ -42,6 +42,8 @@ SYMBOLS = {
     "ebsd_abi_version": (_int, []),
     "ebsd_last_error": (ctypes.c_char_p, []),
     "ebsd_launch_count": (ctypes.c_uint64, []),
+    "ebsd_quantize_crop": (_int, [_c_void_p, _int, _i64, _int, _int, _int, _int, _int, _int, _int, _int, _c_void_p,
+                                  _c_void_p]),
     "ebsd_encoder_create": (_int, [ctypes.POINTER(_c_void_p), ctypes.POINTER(EbsdWeights), _int, _c_void_p]),
     "ebsd_encoder_destroy": (None, [_c_void_p]),
     "ebsd_encoder_workspace_bytes": (_size_t, [_c_void_p, _i64]),

@@ -1,0 +1,98 @@
+// Input transform on the device: 8-bit quantise + centre crop / zero pad to 128 x 128.
+//
+// Replaces create_default_transform (latice/data_module.py:17-33 = ToPILImage -> Grayscale -> CenterCrop ->
+// ToTensor) as applied by DPdataset.__getitem__ (data_module.py:122-133) and encode_pattern(s_batch)
+// (latice/index/dp_indexer.py:124-126, 150-163), up to the uint8 image; ToTensor's k/255 happens inside the encoder.
+//
+//   quantise: (x * 255).astype(uint8) as numpy does it on x86-64 (torchvision to_pil_image): the product is
+//             rounded in the input's own precision, truncated toward zero to a 32-bit integer and the low byte kept;
+//             NaN and |x*255| >= 2^31 give 0 (cvttsd2si overflow pattern 0x80000000).  uint8 input is taken as is.
+//   crop/pad: torchvision center_crop -- the host passes, per axis, the first source index, the first destination
+//             index and the length of the copied span (ebsd_vae_b200/transform.py:_axis_window); the rest is zero.
+#include "common.cuh"
+
+namespace ebsd {
+
+__device__ __forceinline__ uint8_t quantise_f64(double x) {
+    const double v = x * 255.0;
+    if (!(fabs(v) < 2147483648.0)) return 0;
+    return (uint8_t)(int)v;
+}
+__device__ __forceinline__ uint8_t quantise_f32(float x) {
+    const float v = __fmul_rn(x, 255.0f);
+    if (!(fabsf(v) < 2147483648.0f)) return 0;
+    return (uint8_t)(int)v;
+}
+
+struct CropParams {
+    long long B;
+    int H, W;          // source frame
+    int sy, dy, ly;    // rows: source start, destination start, length
+    int sx, dx, lx;    // columns
+};
+
+// one thread = four horizontally adjacent output pixels (one 32-bit store)
+template <int DTYPE>  // 0 = uint8, 1 = float32, 2 = float64
+__global__ void __launch_bounds__(256) quantise_crop_kernel(const void *__restrict__ src, uint8_t *__restrict__ dst,
+                                                            const CropParams p) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = p.B * 128 * 32;
+    if (gid >= total) return;
+    const int q = (int)(gid & 31);
+    const int oy = (int)((gid >> 5) & 127);
+    const long long n = gid >> 12;
+    uint32_t packed = 0u;
+    const int yy = oy - p.dy;
+    if (yy >= 0 && yy < p.ly) {
+        const long long row = (n * p.H + (p.sy + yy)) * p.W;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int xx = q * 4 + j - p.dx;
+            if (xx < 0 || xx >= p.lx) continue;
+            const long long off = row + p.sx + xx;
+            uint8_t v;
+            if (DTYPE == 0) v = ((const uint8_t *)src)[off];
+            else if (DTYPE == 1) v = quantise_f32(((const float *)src)[off]);
+            else v = quantise_f64(((const double *)src)[off]);
+            packed |= (uint32_t)v << (8 * j);
+        }
+    }
+    ((uint32_t *)dst)[gid] = packed;
+}
+
+}  // namespace ebsd
+
+using namespace ebsd;
+
+extern "C" int ebsd_quantize_crop(const void *src, int src_dtype, int64_t B, int H, int W, int sy, int dy, int ly,
+                                  int sx, int dx, int lx, uint8_t *dst, void *stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    EBSD_REQUIRE(src_dtype >= 0 && src_dtype <= 2, "ebsd_quantize_crop: bad dtype %d", src_dtype);
+    EBSD_REQUIRE(B >= 0 && H > 0 && W > 0, "ebsd_quantize_crop: bad shape");
+    EBSD_REQUIRE(ly >= 0 && lx >= 0 && sy >= 0 && sx >= 0 && dy >= 0 && dx >= 0 && sy + ly <= H && sx + lx <= W &&
+                     dy + ly <= 128 && dx + lx <= 128,
+                 "ebsd_quantize_crop: window does not fit (source %dx%d, rows %d+%d->%d, columns %d+%d->%d)", H, W, sy,
+                 ly, dy, sx, lx, dx);
+    if (B == 0) return EBSD_OK;
+    EBSD_REQUIRE(src && dst, "ebsd_quantize_crop: null pointer");
+    EBSD_REQUIRE(((uintptr_t)dst & 3) == 0, "ebsd_quantize_crop: dst must be 4-byte aligned");
+    CropParams p;
+    p.B = B;
+    p.H = H;
+    p.W = W;
+    p.sy = sy;
+    p.dy = dy;
+    p.ly = ly;
+    p.sx = sx;
+    p.dx = dx;
+    p.lx = lx;
+    const long long total = B * 128 * 32;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_dtype == 0) quantise_crop_kernel<0><<<grid, 256, 0, st>>>(src, dst, p);
+    else if (src_dtype == 1) quantise_crop_kernel<1><<<grid, 256, 0, st>>>(src, dst, p);
+    else quantise_crop_kernel<2><<<grid, 256, 0, st>>>(src, dst, p);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}

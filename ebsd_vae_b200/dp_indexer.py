@@ -20,7 +20,7 @@ from numpy.typing import NDArray
 from pydantic.dataclasses import dataclass
 
 from .model import EncoderEngine
-from .transform import load_patterns, parse_rotation_angles, quantise_u8, transform_batch_u8, _axis_window
+from .transform import load_patterns, parse_rotation_angles, transform_batch_device, transform_batch_u8
 from .vector_db import LatentVectorDatabase, LatentVectorDatabaseConfig, OrientationResult
 
 logger = logging.getLogger(__name__)
@@ -85,11 +85,17 @@ class DiffractionPatternIndexer:
                 self._engine = EncoderEngine(self.model.state_dict(), self.device)
         return self._engine
 
-    def _encode_host_tensor(self, t: torch.Tensor) -> torch.Tensor:
-        """Host tensor [B,128,128] (uint8 or float32) -> mu [B,16] on the device.
+    def _encode_host_tensor(self, t: torch.Tensor, transform: bool = False) -> torch.Tensor:
+        """Host tensor [B,H,W] -> mu [B,16] on the device.
 
-        The host -> device copy is pipelined against the encoder: slices of ``ENCODE_CHUNK`` patterns are copied
-        on a side stream into one device buffer while the compute stream encodes the slices that have already
+        ``transform=False``: ``t`` is [B,128,128] uint8 (k/255 encoded) or float32 (used as is) -- tensors bypass the
+        reference's transform (dp_indexer.py:128-131, 165-169).  ``transform=True``: ``t`` is what the reference
+        feeds to ``create_default_transform`` (float32 / float64 / uint8 frames of any size); the 8-bit quantise and
+        the centre crop run on the device (``ebsd_quantize_crop``), so raw frames cross PCIe once and no per-pattern
+        host work remains.
+
+        The host -> device copy is pipelined against the encoder: slices of at most ``ENCODE_CHUNK`` patterns are
+        copied on a side stream into one device buffer while the compute stream works on the slices that have already
         landed (pinned sources copy asynchronously; pageable ones still work, just without the overlap).
         """
         b = t.shape[0]
@@ -115,7 +121,10 @@ class DiffractionPatternIndexer:
                 events.append(ev)
         for i, a in enumerate(range(0, b, step)):
             compute.wait_event(events[i])
-            mu[a : a + step] = self.engine.encode(dev[a : a + step])
+            part = dev[a : a + step]
+            if transform:
+                part = transform_batch_device(part, tuple(self.config.image_size))
+            mu[a : a + step] = self.engine.encode(part)
         return mu
 
     def _encode_u8_host(self, u8: np.ndarray) -> torch.Tensor:
@@ -127,6 +136,12 @@ class DiffractionPatternIndexer:
         if isinstance(patterns, np.ndarray):
             if patterns.ndim not in (2, 3):
                 raise AssertionError(f"Expected 4D tensor, got {patterns.ndim + 1}D")
+            if patterns.ndim == 2:
+                patterns = patterns[None]
+            if patterns.dtype in (np.float32, np.float64, np.uint8):
+                return self._encode_host_tensor(torch.from_numpy(np.ascontiguousarray(patterns)), transform=True)
+            # anything else (float16, integers the reference rejects ...) goes through the host restatement, which
+            # raises the reference's TypeError for unsupported dtypes
             return self._encode_u8_host(transform_batch_u8(patterns, tuple(self.config.image_size)))
         t = patterns
         if t.dim() == 2:
@@ -167,18 +182,15 @@ class DiffractionPatternIndexer:
         angles = parse_rotation_angles(angles_path)
         if len(angles) < len(data):
             raise ValueError(f"angle file has {len(angles)} rows for {len(data)} patterns")
-        th, tw = tuple(self.config.image_size)
-        sy, dy, ly = _axis_window(data.shape[1], th)
-        sx, dx, lx = _axis_window(data.shape[2], tw)
         outs = []
         for a in range(0, len(data), self.ENCODE_CHUNK):
-            window = np.asarray(data[a : a + self.ENCODE_CHUNK, sy : sy + ly, sx : sx + lx]).astype(np.float64)
-            q = quantise_u8(window)
-            if (ly, lx) != (th, tw):
-                full = np.zeros((len(q), th, tw), dtype=np.uint8)
-                full[:, dy : dy + ly, dx : dx + lx] = q
-                q = full
-            outs.append(self._encode_u8_host(np.ascontiguousarray(q)))
+            frames = np.array(data[a : a + self.ENCODE_CHUNK])  # writable copy of the (read-only) memory map slice
+            if frames.dtype not in (np.float64, np.float32, np.uint8, np.int16, np.int32, np.int64):
+                frames = frames.astype(np.float64)  # dtypes torch cannot carry: cast on the host like the reference
+            dev = torch.from_numpy(frames).to(self.device)
+            # DPdataset.__getitem__ casts to float64 before the transform (data_module.py:132); exact on the device too
+            u8 = transform_batch_device(dev.to(torch.float64), tuple(self.config.image_size))
+            outs.append(self.engine.encode(u8))
         latents = torch.cat(outs) if outs else torch.empty((0, 16), dtype=torch.float32, device=self.device)
         return latents, angles[: len(data)]
 

@@ -47,6 +47,34 @@ def transform_batch_u8(patterns: np.ndarray, image_size: tuple[int, int] = (128,
     return out
 
 
+def transform_batch_device(frames, image_size: tuple[int, int] = (128, 128)):
+    """Device version of :func:`transform_batch_u8`: CUDA tensor [B,H,W] (uint8 / float32 / float64) -> uint8
+    [B,128,128] on the same device, bit-identical to the host function (``ebsd_quantize_crop``)."""
+    import torch
+
+    from . import _native
+
+    if tuple(image_size) != (128, 128):
+        raise ValueError("the B200 encoder is specialised for image_size=(128, 128)")
+    if frames.dim() != 3:
+        raise ValueError(f"pic should be 2/3 dimensional. Got {frames.dim()} dimensions.")
+    codes = {torch.uint8: 0, torch.float32: 1, torch.float64: 2}
+    if frames.dtype not in codes:
+        raise TypeError(f"Input type {frames.dtype} is not supported")
+    frames = frames.contiguous()
+    b, h, w = frames.shape
+    sy, dy, ly = _axis_window(h, 128)
+    sx, dx, lx = _axis_window(w, 128)
+    out = torch.empty((b, 128, 128), dtype=torch.uint8, device=frames.device)
+    with torch.cuda.device(frames.device):
+        _native.check(
+            _native.load().ebsd_quantize_crop(frames.data_ptr(), codes[frames.dtype], b, h, w, sy, dy, ly, sx, dx, lx,
+                                              out.data_ptr(), torch.cuda.current_stream(frames.device).cuda_stream),
+            "ebsd_quantize_crop",
+        )
+    return out
+
+
 def parse_rotation_angles(path: str | Path) -> np.ndarray:
     """Angle file -> float64 [N,3] (z1, x, z2 = phi1, Phi, phi2 in degrees).
 

@@ -225,6 +225,64 @@ class LatentVectorDatabase:
         self._latents = self._eulers = self._quats = None
         logger.info("Deleted collection '%s'", self.collection_name)
 
+    # ------------------------------------------------------------------ persistence
+    @property
+    def npz_path(self) -> Path:
+        """``<persist_directory>/<collection_name>.npz`` -- the role of Chroma's ``persist_directory``
+        (chroma_db.py:113-117) and of the FAISS variant's single ``.npz`` file (faiss_db.py:125, 440-476)."""
+        return Path(self.persist_directory) / f"{self.collection_name}.npz"
+
+    def save(self, path: str | Path | None = None) -> Path:
+        """Write the dictionary to one ``.npz``: ``latents`` (fp32 [N,16], rows normalised exactly as searched),
+        ``orientations`` (float64 [N,3] degrees -- the key the reference's FAISS file uses, faiss_db.py:448-455),
+        ``dimension``.  The FAISS file's ``faiss_index`` blob is a serialised third-party object and is not produced."""
+        path = Path(path) if path is not None else self.npz_path
+        path = path.with_suffix(".npz")
+        path.parent.mkdir(parents=True, exist_ok=True)
+        n = self._count
+        lat = self._latents[:n].cpu().numpy() if n else np.zeros((0, self.dimension), np.float32)
+        eul = self._eulers[:n].cpu().numpy() if n else np.zeros((0, 3), np.float64)
+        np.savez_compressed(str(path), latents=lat, orientations=eul, dimension=np.int64(self.dimension))
+        logger.info("Saved %d vectors to %s", n, path)
+        return path
+
+    def load(self, path: str | Path | None = None) -> None:
+        """Replace the in-memory dictionary with the contents of a file written by :meth:`save` (raises
+        ``FileNotFoundError("NPZ file missing.")`` like faiss_db.py:463-465).  Rows are stored normalised;
+        normalising them again on insertion is the identity up to one fp32 rounding, so searches return the same
+        rows (the stored, not the re-normalised, values are used: they are copied verbatim)."""
+        path = Path(path) if path is not None else self.npz_path
+        path = path.with_suffix(".npz")
+        if not path.exists():
+            logger.error("Cannot load. NPZ file %s not found.", path)
+            raise FileNotFoundError("NPZ file missing.")
+        data = np.load(str(path))
+        lat, eul = data["latents"], data["orientations"]
+        if "dimension" in data.files and int(data["dimension"]) != self.dimension:
+            raise ValueError(f"Expected latent vectors of dimension {self.dimension}, got {int(data['dimension'])}")
+        self._validate_vectors(lat, eul)
+        self.delete_collection()
+        n = len(lat)
+        if n == 0:
+            return
+        dev = self._dev()
+        self._reserve(n)
+        self._latents[:n] = torch.from_numpy(np.ascontiguousarray(lat, dtype=np.float32)).to(dev)   # verbatim
+        self._eulers[:n] = torch.from_numpy(np.ascontiguousarray(eul, dtype=np.float64)).to(dev)
+        with torch.cuda.device(dev):
+            _native.check(_native.load().ebsd_euler_to_quat(self._eulers[:n].data_ptr(), n, self._quats[:n].data_ptr(),
+                                                            self._stream(dev)), "ebsd_euler_to_quat")
+        self._count = n
+        logger.info("Loaded %d vectors from %s", n, path)
+
+    def delete_persistence(self) -> None:
+        """Delete the persisted file and reset the in-memory dictionary (faiss_db.py:478-496)."""
+        path = self.npz_path.with_suffix(".npz")
+        if path.exists():
+            path.unlink()
+            logger.info("Deleted index file: %s", path)
+            self.delete_collection()
+
     # ------------------------------------------------------------------ device-level search
     def _prepare_queries(self, query_vectors) -> torch.Tensor:
         dev = self._dev()

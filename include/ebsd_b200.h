@@ -47,6 +47,20 @@ const char *ebsd_last_error(void);
 uint64_t ebsd_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
+ * Input transform: 8-bit quantise + centre crop / zero pad to 128 x 128
+ *   replaces create_default_transform (latice/data_module.py:17-33) as applied by DPdataset.__getitem__
+ *   (data_module.py:122-133) and encode_pattern / encode_patterns_batch (latice/index/dp_indexer.py:124-126,
+ *   150-163), up to the uint8 image (ToTensor's k/255 is applied inside the encoder).
+ * src: [B,H,W] device array, src_dtype 0 = uint8 (copied), 1 = float32, 2 = float64 ((x*255).astype(uint8) with
+ * numpy/x86 semantics: product rounded in the source precision, truncated toward zero, low byte kept; NaN and
+ * |x*255| >= 2^31 give 0).  Rows [sy, sy+ly) of the source go to rows [dy, dy+ly) of the 128-row output, columns
+ * likewise; everything else is zero (torchvision center_crop: see ebsd_vae_b200/transform.py:_axis_window).
+ * dst: uint8 [B,128,128], 4-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+int ebsd_quantize_crop(const void *src, int src_dtype, int64_t B, int H, int W, int sy, int dy, int ly, int sx, int dx,
+                       int lx, uint8_t *dst, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Encoder: VariationalAutoEncoderRawData.encoder + mu / logvar heads
  *   replaces latice/model.py:55-58 (forward up to logvar), layer plan latice/model.py:93-129,
  *   as called from latice/index/dp_indexer.py:133-137, 177-184, 281-287.

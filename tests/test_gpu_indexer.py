@@ -127,3 +127,38 @@ def test_uint8_file_goes_through_float64_cast_like_the_reference(tmp_path, golde
     mu, _ = R.encode(sd, R.u8_to_input(torch.from_numpy(u8)))
     lat = idx.db._latents[:4].cpu().numpy()
     assert np.linalg.norm(lat - T.normalize_rows(mu.numpy()), axis=1).max() < 1e-3
+
+
+def test_dictionary_persistence_round_trip(tmp_path):
+    """save -> load gives the same search results bit for bit; missing files raise like the FAISS class."""
+    import ebsd_vae_b200 as E
+
+    rng = np.random.default_rng(3)
+    lat = rng.normal(size=(3000, 16)).astype(np.float32)
+    lat[100] = lat[7]           # duplicate rows: the tie order must survive the round trip
+    eul = rng.uniform(0, 360, size=(3000, 3))
+    cfg = E.LatentVectorDatabaseConfig(collection_name="persist_test", persist_directory=str(tmp_path))
+    db = E.LatentVectorDatabase(cfg)
+    db.add_vectors(lat, eul)
+    q = rng.normal(size=(50, 16)).astype(np.float32)
+    q[0] = lat[7]
+    before = db.find_best_orientations_batch(q, top_n=10, min_required_matches=3, orientation_threshold=3.0)
+    path = db.save()
+    assert path == tmp_path / "persist_test.npz" and path.exists()
+    saved = np.load(path)
+    assert saved["orientations"].shape == (3000, 3) and saved["orientations"].dtype == np.float64
+
+    db2 = E.LatentVectorDatabase(cfg)
+    db2.load()
+    assert db2.get_count() == 3000
+    after = db2.find_best_orientations_batch(q, top_n=10, min_required_matches=3, orientation_threshold=3.0)
+    np.testing.assert_array_equal(before.indices, after.indices)
+    np.testing.assert_array_equal(before.distances, after.distances)
+    np.testing.assert_array_equal(before.success, after.success)
+    np.testing.assert_array_equal(before.mean_orientations, after.mean_orientations)
+    assert list(before.indices[0][:2]) == [7, 100]
+
+    db2.delete_persistence()
+    assert not path.exists() and db2.get_count() == 0
+    with pytest.raises(FileNotFoundError, match="NPZ file missing."):
+        db2.load()
