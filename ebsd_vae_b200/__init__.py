@@ -6,10 +6,12 @@ Drop-in names (reference: poyentung/ebsd-vae, package ``latice``):
 * ``LatentVectorDatabase`` (= ``ChromaLatentVectorDatabase``), ``LatentVectorDatabaseConfig``,
   ``OrientationResult``                                      (latice/index/chroma_db.py)
 * ``VariationalAutoEncoderRawData``                          (latice/model.py)
+* ``get_color_key``                                          (latice/utils/utils.py:206-240, IPF colours)
 
 All compute runs in libebsd_b200.so (hand-written sm_100a CUDA behind a C ABI, include/ebsd_b200.h).
 There is no CPU or eager-PyTorch fallback.
 """
+from .colorkey import get_color_key, ipf_colors_device
 from .dp_indexer import DiffractionPatternIndexer, IndexerConfig
 from .model import EncoderEngine, VariationalAutoEncoderRawData, load_vae_weights
 from .vector_db import (
@@ -31,4 +33,6 @@ __all__ = [
     "LatentVectorDatabaseConfig",
     "OrientationResult",
     "OrientationResultBatch",
+    "get_color_key",
+    "ipf_colors_device",
 ]

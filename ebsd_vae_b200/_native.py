@@ -60,6 +60,7 @@ SYMBOLS = {
                          _size_t, _c_void_p]),
     "ebsd_topk_merge": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "ebsd_euler_to_quat": (_int, [_c_void_p, _i64, _c_void_p, _c_void_p]),
+    "ebsd_ipf_color": (_int, [_c_void_p, _i64, _int, _c_void_p, _c_void_p]),
     "ebsd_consensus": (_int, [_c_void_p, _i64, _c_void_p, _i64, _int, ctypes.c_double, _int, _int, _int, _int,
                               _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
 }

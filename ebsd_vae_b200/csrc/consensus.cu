@@ -255,21 +255,122 @@ __global__ void __launch_bounds__(256) consensus_kernel(const ConsensusParams p)
     }
 }
 
-__global__ void euler_to_quat_kernel(const double *euler_deg, long long n, double *quat) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// scipy R.from_euler("zxz", [a, b, c], degrees=True) as a quaternion (x, y, z, w): extrinsic, R = Rz(c) Rx(b) Rz(a)
+__device__ __forceinline__ Quat euler_zxz_to_quat(double a_deg, double b_deg, double c_deg) {
     const double kRad = 3.14159265358979323846 / 180.0;
-    const double a = euler_deg[i * 3 + 0] * kRad, b = euler_deg[i * 3 + 1] * kRad, c = euler_deg[i * 3 + 2] * kRad;
+    const double a = a_deg * kRad, b = b_deg * kRad, c = c_deg * kRad;
     double sb, cb, sp, cp, sm, cm;
     sincos(0.5 * b, &sb, &cb);
     sincos(0.5 * (a + c), &sp, &cp);
     sincos(0.5 * (a - c), &sm, &cm);
-    double4 q;
-    q.x = sb * cm;
-    q.y = -sb * sm;
-    q.z = cb * sp;
-    q.w = cb * cp;
-    *(double4 *)(quat + i * 4) = q;
+    return Quat{sb * cm, -sb * sm, cb * sp, cb * cp};
+}
+
+__global__ void euler_to_quat_kernel(const double *euler_deg, long long n, double *quat) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Quat q = euler_zxz_to_quat(euler_deg[i * 3 + 0], euler_deg[i * 3 + 1], euler_deg[i * 3 + 2]);
+    *(double4 *)(quat + i * 4) = make_double4(q.x, q.y, q.z, q.w);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// IPF colour key: get_color_key (latice/utils/utils.py:206-240) +
+// ColorKeyGenerator.generate_ipf_color (latice/utils/colorkey.py:64-130).  One thread per orientation, float64,
+// products and sums un-fused in the reference's order so that the unit-triangle decisions agree.
+// ---------------------------------------------------------------------------------------------------------------
+// QUAT_SYM.as_matrix() (scipy, row-major 3x3 per operator) for the table above, to 17 significant digits
+__constant__ double c_cubic_mat[24][9] = {
+    {1.0, 0.0, 0.0, 0.0, -1.0, 0.0, 0.0, 0.0, -1.0},
+    {-1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, -1.0},
+    {-1.0, 0.0, 0.0, 0.0, -1.0, 0.0, 0.0, 0.0, 1.0},
+    {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0},
+    {0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, 1.0, 0.0},
+    {0.0, -1.0, 0.0, 0.0, 0.0, 1.0, -1.0, 0.0, 0.0},
+    {0.0, 1.0, 0.0, 0.0, 0.0, -1.0, -1.0, 0.0, 0.0},
+    {0.0, 0.0, 1.0, -1.0, 0.0, 0.0, 0.0, -1.0, 0.0},
+    {0.0, -1.0, 0.0, 0.0, 0.0, -1.0, 1.0, 0.0, 0.0},
+    {0.0, 0.0, -1.0, 1.0, 0.0, 0.0, 0.0, -1.0, 0.0},
+    {0.0, 0.0, -1.0, -1.0, 0.0, 0.0, 0.0, 1.0, 0.0},
+    {0.0, 1.0, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0, 0.0},
+    {0.0, 1.0000000000000002, 0.0, 1.0000000000000002, 0.0, 0.0, 0.0, 0.0, -1.0000000000000002},
+    {0.0, 0.0, 1.0000000000000002, 0.0, -1.0000000000000002, 0.0, 1.0000000000000002, 0.0, 0.0},
+    {1.0000000000000002, 0.0, 0.0, 0.0, 0.0, -1.0000000000000002, 0.0, 1.0000000000000002, 0.0},
+    {0.0, -1.0000000000000002, 0.0, -1.0000000000000002, 0.0, -0.0, 0.0, 0.0, -1.0000000000000002},
+    {0.0, 0.0, -1.0000000000000002, 0.0, -1.0000000000000002, -0.0, -1.0000000000000002, 0.0, 0.0},
+    {1.0000000000000002, 0.0, 0.0, 0.0, 0.0, 1.0000000000000002, 0.0, -1.0000000000000002, 0.0},
+    {-1.0000000000000002, 0.0, 0.0, 0.0, 0.0, 1.0000000000000002, 0.0, 1.0000000000000002, 0.0},
+    {-1.0000000000000002, -0.0, 0.0, 0.0, 0.0, -1.0000000000000002, 0.0, -1.0000000000000002, 0.0},
+    {0.0, -1.0000000000000002, 0.0, 1.0000000000000002, 0.0, 0.0, 0.0, 0.0, 1.0000000000000002},
+    {0.0, 1.0000000000000002, 0.0, -1.0000000000000002, 0.0, -0.0, -0.0, 0.0, 1.0000000000000002},
+    {0.0, 0.0, 1.0000000000000002, 0.0, 1.0000000000000002, 0.0, -1.0000000000000002, 0.0, 0.0},
+    {0.0, -0.0, -1.0000000000000002, 0.0, 1.0000000000000002, -0.0, 1.0000000000000002, 0.0, 0.0},
+};
+
+__device__ __forceinline__ double dot3_unfused(const double *m, double x, double y, double z) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dmul_rn(m[1], y)), __dmul_rn(m[2], z));
+}
+
+__global__ void ipf_color_kernel(const double *__restrict__ euler_deg, long long n, int row, uint8_t *__restrict__ rgb) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Quat q = euler_zxz_to_quat(euler_deg[i * 3 + 0], euler_deg[i * 3 + 1], euler_deg[i * 3 + 2]);
+    // scipy as_matrix of a unit quaternion, row `row`
+    const double x2 = __dmul_rn(q.x, q.x), y2 = __dmul_rn(q.y, q.y), z2 = __dmul_rn(q.z, q.z), w2 = __dmul_rn(q.w, q.w);
+    const double xy = __dmul_rn(q.x, q.y), zw = __dmul_rn(q.z, q.w), xz = __dmul_rn(q.x, q.z), yw = __dmul_rn(q.y, q.w);
+    const double yz = __dmul_rn(q.y, q.z), xw = __dmul_rn(q.x, q.w);
+    double px, py, pz;
+    if (row == 0) {
+        px = __dadd_rn(__dsub_rn(__dsub_rn(x2, y2), z2), w2);
+        py = __dmul_rn(2.0, __dsub_rn(xy, zw));
+        pz = __dmul_rn(2.0, __dadd_rn(xz, yw));
+    } else if (row == 1) {
+        px = __dmul_rn(2.0, __dadd_rn(xy, zw));
+        py = __dadd_rn(__dsub_rn(__dadd_rn(-x2, y2), z2), w2);
+        pz = __dmul_rn(2.0, __dsub_rn(yz, xw));
+    } else {
+        px = __dmul_rn(2.0, __dsub_rn(xz, yw));
+        py = __dmul_rn(2.0, __dadd_rn(yz, xw));
+        pz = __dadd_rn(__dadd_rn(__dsub_rn(-x2, y2), z2), w2);
+    }
+    const double nrm = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)), __dmul_rn(pz, pz)));
+    px = px / nrm;
+    py = py / nrm;
+    pz = pz / nrm;
+    const double eta_max = 45.0 * (3.14159265358979323846 / 180.0);
+    const double chi_lim = acos(1.0 / sqrt(3.0));
+    double chi = 0.0, eta = 0.0;
+    for (int c = 0; c < 48; ++c) {
+        const double *m = c_cubic_mat[c % 24];
+        double vx = dot3_unfused(m, px, py, pz), vy = dot3_unfused(m + 3, px, py, pz), vz = dot3_unfused(m + 6, px, py, pz);
+        if (c >= 24) {
+            vx = -vx;
+            vy = -vy;
+            vz = -vz;
+        }
+        if (vz < 0) {  // USE_INVERSION (latice/utils/constants.py:11)
+            vx = -vx;
+            vy = -vy;
+            vz = -vz;
+        }
+        chi = acos(fmin(1.0, fmax(-1.0, vz)));
+        eta = atan2(vy, vx);
+        if (!(eta < 0 || eta > eta_max || chi < 0 || chi > chi_lim)) break;
+    }
+    const double k = 180.0 / 3.14159265358979323846;
+    const double chi_max = chi_lim * k;
+    const double eta_deg = eta * k, chi_deg = chi * k;
+    double r = 1.0 - chi_deg / chi_max, b = fabs(eta_deg - 0.0) / 45.0;
+    double g = 1.0 - b;
+    g = g * (chi_deg / chi_max);
+    b = b * (chi_deg / chi_max);
+    r = sqrt(r);
+    g = sqrt(g);
+    b = sqrt(b);
+    const double mx = fmax(r, fmax(g, b));
+    // Python round(): half to even, exactly what rint does in the default rounding mode
+    rgb[i * 3 + 0] = (uint8_t)(int)rint(255.0 * r / mx);
+    rgb[i * 3 + 1] = (uint8_t)(int)rint(255.0 * g / mx);
+    rgb[i * 3 + 2] = (uint8_t)(int)rint(255.0 * b / mx);
 }
 
 }  // namespace ebsd
@@ -288,6 +389,20 @@ int ebsd_euler_to_quat(const double *euler_deg, int64_t n, double *quat, void *s
     const int threads = 256;
     euler_to_quat_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(euler_deg, n,
                                                                                                        quat);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}
+
+int ebsd_ipf_color(const double *euler_deg, int64_t n, int axis, uint8_t *rgb, void *stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    EBSD_REQUIRE(n >= 0, "ebsd_ipf_color: negative n");
+    EBSD_REQUIRE(axis >= 0 && axis <= 2, "ebsd_ipf_color: axis must be 0 (ipf_x), 1 (ipf_y) or 2 (ipf_z), got %d", axis);
+    if (n == 0) return EBSD_OK;
+    EBSD_REQUIRE(euler_deg && rgb, "ebsd_ipf_color: null pointer");
+    const int threads = 128;
+    ipf_color_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(euler_deg, n, axis,
+                                                                                                   rgb);
     EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }

@@ -142,6 +142,15 @@ int ebsd_consensus(const double *quat_table, int64_t N, const int64_t *cand_idx,
                    double *mean_quat, double *mean_euler_deg, uint8_t *success, uint64_t *similar_mask,
                    int32_t *ref_iter, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * IPF colour key of orientations (orientation maps)
+ *   replaces get_color_key (latice/utils/utils.py:206-240) + ColorKeyGenerator.generate_ipf_color
+ *   (latice/utils/colorkey.py:64-130).
+ * euler_deg [n,3] float64 (scipy "zxz" extrinsic, degrees); axis 0 / 1 / 2 = mode "ipf_x" / "ipf_y" / "ipf_z" (the row
+ * of the rotation matrix used as pole); rgb [n,3] uint8.
+ * ------------------------------------------------------------------------------------------- */
+int ebsd_ipf_color(const double *euler_deg, int64_t n, int axis, uint8_t *rgb, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
