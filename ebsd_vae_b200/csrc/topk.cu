@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "topk_screen.cuh"
 
 namespace ebsd {
 
@@ -364,6 +365,80 @@ __global__ void normalize_rows_kernel(float *x, long long n) {
     }
 }
 
+// Re-rank of the screen's survivors (topk_screen.cuh): one warp per query, canonical fp32 dots, the exact kernel's
+// (dot desc, row asc) list.  A buffer flagged -1 (more than CAP rows within 2 EPS of the k-th best) is replaced by a
+// brute-force scan of the rows that buffer covers.
+__device__ __forceinline__ float canonical_dot(const float4 (&q)[4], const float *__restrict__ row) {
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float4 d = __ldg((const float4 *)row + c);
+        a = fmaf(q[c].x, d.x, a);
+        a = fmaf(q[c].y, d.y, a);
+        a = fmaf(q[c].z, d.z, a);
+        a = fmaf(q[c].w, d.w, a);
+    }
+    return a;
+}
+
+__global__ void __launch_bounds__(256) topk_rerank_kernel(const float *__restrict__ dict, const float *__restrict__ queries,
+                                                          const ScreenParams p, long long index_base,
+                                                          float *__restrict__ out_dot, long long *__restrict__ out_idx,
+                                                          float *__restrict__ out_dist) {
+    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= p.Q) return;
+    float4 qv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) qv[c] = __ldg((const float4 *)(queries + q * kD) + c);
+    const int qt = (int)(q / kScrM), m = (int)(q % kScrM);
+    const long long total_tiles = (p.N + kScrN - 1) / kScrN;
+    float e_dot = -INFINITY;
+    int e_idx = kIdxEmpty;
+    for (int split = 0; split < p.n_splits; ++split) {
+        const int item = split * p.n_qtiles + qt;
+        for (int half = 0; half < 2; ++half) {
+            const long long slot = ((long long)item * 2 + half) * kScrM + m;
+            const int n = p.cand_n[slot];
+            if (n >= 0) {
+                for (int base = 0; base < n; base += 32) {
+                    const int j = base + lane;
+                    int row = kIdxEmpty;
+                    float d = -INFINITY;
+                    if (j < n) {
+                        row = p.cand_i[slot * kScrCap + j];
+                        d = canonical_dot(qv, dict + (long long)row * kD);
+                    }
+                    const int cnt = n - base < 32 ? n - base : 32;
+                    for (int j2 = 0; j2 < cnt; ++j2)
+                        warp_insert<int>(e_dot, e_idx, __shfl_sync(0xffffffffu, d, j2), __shfl_sync(0xffffffffu, row, j2), lane);
+                }
+            } else {
+                const long long tile0 = (long long)split * p.tiles_per_split;
+                long long tile1 = tile0 + p.tiles_per_split;
+                if (tile1 > total_tiles) tile1 = total_tiles;
+                for (long long t = tile0; t < tile1; ++t)
+                    for (int c0 = 0; c0 < 128; c0 += 32) {
+                        const long long row = t * kScrN + half * 128 + c0 + lane;
+                        const float d = row < p.N ? canonical_dot(qv, dict + row * kD) : -INFINITY;
+                        const float kth = __shfl_sync(0xffffffffu, e_dot, p.k - 1);
+                        unsigned mask = __ballot_sync(0xffffffffu, row < p.N && d >= kth);
+                        while (mask) {
+                            const int src = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            warp_insert<int>(e_dot, e_idx, __shfl_sync(0xffffffffu, d, src), (int)(t * kScrN + half * 128 + c0 + src), lane);
+                        }
+                    }
+            }
+        }
+    }
+    if (lane < p.k) {
+        out_dot[q * p.k + lane] = e_dot;
+        out_idx[q * p.k + lane] = e_idx == kIdxEmpty ? -1ll : index_base + e_idx;
+        if (out_dist) out_dist[q * p.k + lane] = 1.0f - e_dot;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 struct TopkPlan {
     int tq;               // queries per thread (8 or 1)
@@ -419,6 +494,86 @@ static TopkPlan make_plan(long long N, long long Q, int sms) {
     return pl;
 }
 
+// ---- tensor-core screen (topk_screen.cuh): plan, workspace carving, launch
+struct ScreenPlan {
+    int n_qtiles, n_splits, tiles_per_split, items;
+    size_t off_dpairs, off_qpairs, off_cs, off_ci, off_cn, off_parts, bytes;
+};
+
+// Rows of the seeding search.  With tau0 the k-th best of N/8 rows a query keeps about 8k survivors over the whole
+// dictionary (k / n0 per row), spread over its buffers: the CAP-entry buffers practically never fill, so the costly
+// in-place compaction stays an exception; the seeding search itself costs 1/8 of a CUDA-core search.
+static long long screen_prefix_rows(long long N) {
+    long long n0 = N / 8;
+    if (n0 < 4096) n0 = 4096;
+    return n0 < N ? n0 : N;
+}
+
+static bool screen_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("EBSD_TOPK_SCREEN");
+        on = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return on == 1;
+}
+
+// The screen pays off once there are enough (query, row) pairs to amortise the operand conversion and the re-rank.
+static bool screen_applies(long long N, long long Q, int k) {
+    // measured (profiles/README.md): the screen is bound by draining the accumulators from TMEM (one fp32 per pair,
+    // ~2 us per 128 x 256 tile) and wins over the CUDA-core kernel only for large dictionaries
+    return screen_enabled() && k < kScrCap / 2 && N >= 400000 && Q >= 1024 && N < 0x7fffff00ll;
+}
+
+static ScreenPlan make_screen_plan(long long N, long long Q, int sms) {
+    ScreenPlan pl;
+    pl.n_qtiles = (int)((Q + kScrM - 1) / kScrM);
+    const long long total_tiles = (N + kScrN - 1) / kScrN;
+    long long s = (2ll * sms + pl.n_qtiles - 1) / pl.n_qtiles;          // aim at two waves of work items
+    if (s > total_tiles / 8) s = total_tiles / 8;                         // at least 8 tiles per split
+    if (s > 2048 / pl.n_qtiles) s = 2048 / pl.n_qtiles;                   // bounds the candidate buffers (~128 KiB/item)
+    if (s < 1) s = 1;
+    pl.tiles_per_split = (int)((total_tiles + s - 1) / s);
+    pl.n_splits = (int)((total_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split);
+    pl.items = pl.n_qtiles * pl.n_splits;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t r = off;
+        off += (bytes + 1023) & ~(size_t)1023;
+        return r;
+    };
+    const size_t slots = (size_t)pl.items * 2 * kScrM;
+    pl.off_dpairs = take((size_t)total_tiles * kScrN * kScrRowB);      // padded to whole tiles
+    pl.off_qpairs = take((size_t)pl.n_qtiles * kScrM * kScrRowB);
+    pl.off_cs = take(slots * kScrCap * sizeof(float));
+    pl.off_ci = take(slots * kScrCap * sizeof(int));
+    pl.off_cn = take(slots * sizeof(int));
+    const TopkPlan ex = make_plan(screen_prefix_rows(N), Q, sms);   // partial lists of the seeding search
+    pl.off_parts = take(ex.n_splits > 1 ? (size_t)ex.n_splits * (size_t)Q * 32 * sizeof(Entry) : 1024);
+    pl.bytes = off + 1024;
+    return pl;
+}
+
+static int make_pairs_map(CUtensorMap *map, const void *base, long long rows, int box_rows) {
+    tensormap_encode_fn encode = get_tensormap_encode();
+    if (!encode) {
+        set_error("ebsd_topk: cuTensorMapEncodeTiled entry point not available");
+        return EBSD_ERR_CUDA;
+    }
+    const cuuint64_t gdim[2] = {32, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)kScrRowB};
+    const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)base, gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("ebsd_topk: cuTensorMapEncodeTiled(fp16 pairs) failed with %d", (int)cr);
+        return EBSD_ERR_CUDA;
+    }
+    return EBSD_OK;
+}
+
 template <int TQ>
 static int launch_topk(const CUtensorMap &map, const TopkParams &p, int sms, cudaStream_t st) {
     using S = Smem<TQ>;
@@ -431,6 +586,102 @@ static int launch_topk(const CUtensorMap &map, const TopkParams &p, int sms, cud
     const int slots = sms * (TQ <= 4 ? 2 : 1);  // resident CTAs
     const int grid = n_items < slots ? n_items : slots;
     topk_kernel<TQ><<<grid, kThreads, S::alloc, st>>>(map, p);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}
+
+// The exact CUDA-core search of `N` rows (workspace: n_splits * Q * k entries when the plan splits the dictionary).
+static int run_exact(const float *dict, long long N, long long index_base, const float *queries, long long Q, int k,
+                     float *out_dot, long long *out_idx, float *out_dist, void *workspace, int sms, cudaStream_t st) {
+    const TopkPlan pl = make_plan(N, Q, sms);
+    tensormap_encode_fn encode = get_tensormap_encode();
+    if (!encode) {
+        set_error("ebsd_topk: cuTensorMapEncodeTiled entry point not available");
+        return EBSD_ERR_CUDA;
+    }
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = {(cuuint64_t)kD, (cuuint64_t)N};
+    const cuuint64_t gstride[1] = {(cuuint64_t)(kD * 4)};
+    const cuuint32_t box[2] = {(cuuint32_t)kD, (cuuint32_t)kTileRows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)dict, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("ebsd_topk: cuTensorMapEncodeTiled failed with %d", (int)cr);
+        return EBSD_ERR_CUDA;
+    }
+    TopkParams p;
+    p.queries = queries;
+    p.Q = Q;
+    p.N = N;
+    p.index_base = index_base;
+    p.k = k;
+    p.n_qtiles = pl.n_qtiles;
+    p.n_splits = pl.n_splits;
+    p.tiles_per_split = pl.tiles_per_split;
+    p.parts = (Entry *)workspace;
+    p.out_dot = out_dot;
+    p.out_idx = out_idx;
+    p.out_dist = out_dist;
+    int rc = pl.tq == 8 ? launch_topk<8>(map, p, sms, st)
+                        : (pl.tq == 4 ? launch_topk<4>(map, p, sms, st) : launch_topk<1>(map, p, sms, st));
+    if (rc) return rc;
+    if (pl.n_splits > 1) {
+        const int wpb = 8;
+        topk_merge_parts_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, st>>>(p.parts, pl.n_splits, Q, k, index_base,
+                                                                                    out_dot, out_idx, out_dist);
+        EBSD_LAUNCH_CHECK();
+    }
+    return EBSD_OK;
+}
+
+static int run_screen(const float *dict, long long N, long long index_base, const float *queries, long long Q, int k,
+                      float *out_dot, long long *out_idx, float *out_dist, void *workspace, int sms, cudaStream_t st) {
+    const ScreenPlan pl = make_screen_plan(N, Q, sms);
+    uint8_t *ws = (uint8_t *)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    __half *dpairs = (__half *)(ws + pl.off_dpairs);
+    __half *qpairs = (__half *)(ws + pl.off_qpairs);
+    const long long total_tiles = (N + kScrN - 1) / kScrN;
+    const long long drows = total_tiles * kScrN, qrows = (long long)pl.n_qtiles * kScrM;
+    // operands as fp16 (hi | lo) pairs; the padding rows of the last tile are zero
+    EBSD_CUDA_TRY(cudaMemsetAsync(dpairs + N * 32, 0, (size_t)(drows - N) * kScrRowB, st));
+    EBSD_CUDA_TRY(cudaMemsetAsync(qpairs + Q * 32, 0, (size_t)(qrows - Q) * kScrRowB, st));
+    split_rows_f16_kernel<<<(unsigned)((N * 16 + 255) / 256), 256, 0, st>>>(dict, dpairs, N);
+    EBSD_LAUNCH_CHECK();
+    split_rows_f16_kernel<<<(unsigned)((Q * 16 + 255) / 256), 256, 0, st>>>(queries, qpairs, Q);
+    EBSD_LAUNCH_CHECK();
+    CUtensorMap map_d, map_q;
+    int rc;
+    if ((rc = make_pairs_map(&map_d, dpairs, drows, kScrN))) return rc;
+    if ((rc = make_pairs_map(&map_q, qpairs, qrows, kScrM))) return rc;
+    // Seed every query's threshold with its exact k-th best dot over a PREFIX of the dictionary (CUDA-core kernel,
+    // 1/8 of the rows): k rows are then known to have s >= tau0, so rows with s~ < tau0 - EPS can be dropped from
+    // the first tile on and the survivor buffers almost never fill up.  out_dot is reused as scratch for tau0.
+    const long long n0 = screen_prefix_rows(N);
+    if ((rc = run_exact(dict, n0, index_base, queries, Q, k, out_dot, out_idx, nullptr, ws + pl.off_parts, sms, st))) return rc;
+    ScreenParams p;
+    p.Q = Q;
+    p.N = N;
+    p.k = k;
+    p.n_qtiles = pl.n_qtiles;
+    p.n_splits = pl.n_splits;
+    p.tiles_per_split = pl.tiles_per_split;
+    p.tau0 = out_dot;
+    p.cand_s = (float *)(ws + pl.off_cs);
+    p.cand_i = (int *)(ws + pl.off_ci);
+    p.cand_n = (int *)(ws + pl.off_cn);
+    static bool configured = false;
+    if (!configured) {
+        EBSD_CUDA_TRY(cudaFuncSetAttribute(topk_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScrSmem));
+        configured = true;
+    }
+    const int grid = pl.items < sms ? pl.items : sms;
+    topk_screen_kernel<<<grid, kScrThreads, kScrSmem, st>>>(map_d, map_q, p);
+    EBSD_LAUNCH_CHECK();
+    const int wpb = 8;
+    topk_rerank_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, st>>>(dict, queries, p, index_base, out_dot, out_idx,
+                                                                          out_dist);
     EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }
@@ -457,6 +708,7 @@ int ebsd_normalize_rows(float *x, int64_t n, int d, void *stream) {
 
 size_t ebsd_topk_workspace_bytes(int64_t N, int64_t Q, int k) {
     if (N <= 0 || Q <= 0 || k <= 0) return 0;
+    if (screen_applies(N, Q, k)) return make_screen_plan(N, Q, sm_count()).bytes;
     const TopkPlan pl = make_plan(N, Q, sm_count());
     return pl.n_splits > 1 ? (size_t)pl.n_splits * (size_t)Q * (size_t)k * sizeof(Entry) : 0;
 }
@@ -484,54 +736,21 @@ int ebsd_topk(const float *dict, int64_t N, int64_t index_base, const float *que
     EBSD_REQUIRE(((uintptr_t)dict & 15) == 0, "ebsd_topk: dict must be 16-byte aligned");
 
     const int sms = sm_count();
+    if (screen_applies(N, Q, k)) {
+        const size_t need_s = make_screen_plan(N, Q, sms).bytes;
+        if (workspace == nullptr || workspace_bytes < need_s) {
+            set_error("ebsd_topk: workspace too small (%zu < %zu)", workspace_bytes, need_s);
+            return EBSD_ERR_WORKSPACE;
+        }
+        return run_screen(dict, N, index_base, queries, Q, k, out_dot, (long long *)out_idx, out_dist, workspace, sms, st);
+    }
     const TopkPlan pl = make_plan(N, Q, sms);
     const size_t need = pl.n_splits > 1 ? (size_t)pl.n_splits * (size_t)Q * (size_t)k * sizeof(Entry) : 0;
     if (need > 0 && (workspace == nullptr || workspace_bytes < need)) {
         set_error("ebsd_topk: workspace too small (%zu < %zu)", workspace_bytes, need);
         return EBSD_ERR_WORKSPACE;
     }
-
-    tensormap_encode_fn encode = get_tensormap_encode();
-    if (!encode) {
-        set_error("ebsd_topk: cuTensorMapEncodeTiled entry point not available");
-        return EBSD_ERR_CUDA;
-    }
-    CUtensorMap map;
-    const cuuint64_t gdim[2] = {(cuuint64_t)kD, (cuuint64_t)N};
-    const cuuint64_t gstride[1] = {(cuuint64_t)(kD * 4)};
-    const cuuint32_t box[2] = {(cuuint32_t)kD, (cuuint32_t)kTileRows};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)dict, gdim, gstride, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) {
-        set_error("ebsd_topk: cuTensorMapEncodeTiled failed with %d", (int)cr);
-        return EBSD_ERR_CUDA;
-    }
-
-    TopkParams p;
-    p.queries = queries;
-    p.Q = Q;
-    p.N = N;
-    p.index_base = index_base;
-    p.k = k;
-    p.n_qtiles = pl.n_qtiles;
-    p.n_splits = pl.n_splits;
-    p.tiles_per_split = pl.tiles_per_split;
-    p.parts = (Entry *)workspace;
-    p.out_dot = out_dot;
-    p.out_idx = (long long *)out_idx;
-    p.out_dist = out_dist;
-    rc = pl.tq == 8 ? launch_topk<8>(map, p, sms, st)
-                    : (pl.tq == 4 ? launch_topk<4>(map, p, sms, st) : launch_topk<1>(map, p, sms, st));
-    if (rc) return rc;
-    if (pl.n_splits > 1) {
-        const int wpb = 8;
-        topk_merge_parts_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, st>>>(
-            p.parts, pl.n_splits, Q, k, index_base, out_dot, (long long *)out_idx, out_dist);
-        EBSD_LAUNCH_CHECK();
-    }
-    return EBSD_OK;
+    return run_exact(dict, N, index_base, queries, Q, k, out_dot, (long long *)out_idx, out_dist, workspace, sms, st);
 }
 
 int ebsd_topk_merge(const float *dots, const int64_t *idx, int R, int64_t Q, int k, float *out_dot,

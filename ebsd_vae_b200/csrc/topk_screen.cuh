@@ -1,0 +1,264 @@
+// K2s: tensor-core SCREEN for the exact top-k.
+//
+// The exact search ranks rows by the canonical fp32 dot s = q.d (fma chain, oracle/topk_ref.c).  On CUDA cores that
+// costs 16 FMAs per (query, row) pair and is bound by the fp32 pipe (topk_kernel, ~42 TFLOP/s).  Here the tensor
+// cores compute an APPROXIMATE dot s~ for every pair, only pairs that can still matter survive, and the survivors are
+// re-ranked with the canonical arithmetic -- the final lists are bit-identical to the exact kernel's.
+//
+//   operands   rows and queries as fp16 pairs [hi(16) | lo(16)] (64-byte K-major rows, SWIZZLE_64B): x = hi + lo up
+//              to 2^-22 |x|;  s~ = q_hi.d_hi + q_hi.d_lo + q_lo.d_hi  = three tcgen05.mma (M = 128 queries,
+//              N = 256 rows, K = 16 each) into one fp32 TMEM accumulator.
+//   error      |s~ - s| <= EPS = 1e-5 for unit vectors: split remainders (<= 4 * 2^-24), fp16 underflow of the lo parts
+//              (<= 16 * 2^-25), 48 fp32 accumulations in the tensor core (<= 48 * 2^-23 even if it truncates) and the
+//              rounding of the canonical chain itself (<= 16 * 2^-24); tests measure the actual maximum (~3e-7).
+//   filter     a query keeps every row with s~ >= thr.  thr starts at tau0 - EPS, tau0 = the query's exact k-th best dot
+//              over a prefix of the dictionary (found by the CUDA-core kernel first), and is raised whenever a
+//              survivor buffer fills up: thr = (k-th largest s~ among rows already kept) - 2 EPS.
+//              Those k rows have s >= kth - EPS, so the final k-th best exact dot S_k >= kth - EPS, and a dropped row
+//              has s <= s~ + EPS < kth - EPS <= S_k: it cannot be in the top-k, ties included.
+//   layout     TMEM lane = query, column = dictionary row: an epilogue thread owns one query (its threshold lives in
+//              a register) and scans 128 columns per tile; survivors go to a per-(work item, column half, query)
+//              buffer of CAP entries in global memory; a full buffer is compacted in place (k-th largest -> new thr).
+//   re-rank    topk_rerank_kernel: one warp per query gathers the surviving rows of all its buffers, recomputes the
+//              canonical fp32 dot and inserts into the (dot desc, row asc) sorted list of the exact kernel.
+#pragma once
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "tcgen05.cuh"
+
+namespace ebsd {
+
+constexpr int kScrM = 128;           // queries per work item (TMEM lanes)
+constexpr int kScrN = 256;           // dictionary rows per tile (TMEM columns of one accumulator)
+constexpr int kScrRowB = 64;         // bytes per operand row: 16 fp16 hi | 16 fp16 lo
+constexpr int kScrTileB = kScrN * kScrRowB;   // 16 KiB
+constexpr int kScrQB = kScrM * kScrRowB;      // 8 KiB
+constexpr int kScrStages = 6;
+constexpr int kScrCap = 64;          // survivors a buffer holds before it is compacted (> EBSD_MAX_TOPK)
+constexpr float kScrEps = 1e-5f;
+constexpr int kScrThreads = 384;     // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4..11 epilogue (lane quarter x column half)
+constexpr int kScrSmem = 1024 + kScrStages * kScrTileB + kScrQB + 256;
+
+struct ScreenParams {
+    long long Q, N;
+    int k;
+    int n_qtiles, n_splits, tiles_per_split;
+    const float *tau0;  // [Q][k]: exact top-k dots of a dictionary prefix (column k-1 seeds the threshold)
+    float *cand_s;      // [items][2][128][CAP] approximate dots
+    int *cand_i;        // [items][2][128][CAP] shard-local rows
+    int *cand_n;        // [items][2][128]      entries used
+};
+
+// fp32 rows [n,16] -> fp16 pairs [n][hi(16) | lo(16)]
+__global__ void split_rows_f16_kernel(const float *__restrict__ x, __half *__restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 16) return;
+    const long long r = i >> 4;
+    const int c = (int)(i & 15);
+    const float v = x[i];
+    const __half h = __float2half_rn(v);
+    out[r * 32 + c] = h;
+    out[r * 32 + 16 + c] = __float2half_rn(v - __half2float(h));
+}
+
+// k-th largest of vals[0..n) (n <= kScrCap, k <= n): repeated maximum below the previous one, counting duplicates.
+__device__ __noinline__ float kth_largest(const float *vals, int n, int k) {
+    float bound = INFINITY;
+    int taken = 0;
+    for (;;) {
+        float best = -INFINITY;
+        int cnt = 0;
+        for (int i = 0; i < n; ++i) {
+            const float v = vals[i];
+            if (v < bound) {
+                if (v > best) {
+                    best = v;
+                    cnt = 1;
+                } else if (v == best) {
+                    ++cnt;
+                }
+            }
+        }
+        taken += cnt;
+        if (taken >= k || cnt == 0) return best;
+        bound = best;
+    }
+}
+
+__global__ void __launch_bounds__(kScrThreads, 1)
+topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_q,
+                   const ScreenParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem_d = smem;
+    uint8_t *smem_q = smem + kScrStages * kScrTileB;
+    uint64_t *d_full = (uint64_t *)(smem_q + kScrQB);   // [stages]
+    uint64_t *d_empty = d_full + kScrStages;            // [stages]
+    uint64_t *q_full = d_empty + kScrStages;            // [1]
+    uint64_t *q_empty = q_full + 1;                     // [1]
+    uint64_t *tfull = q_empty + 1;                      // [2]
+    uint64_t *tempty = tfull + 2;                       // [2]
+    uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kScrStages; ++s) {
+            mbar_init(&d_full[s], 1);
+            mbar_init(&d_empty[s], 1);
+        }
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], 8);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&map_d);
+        tma_prefetch_desc(&map_q);
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long long total_tiles = (p.N + kScrN - 1) / kScrN;
+    const int n_items = p.n_qtiles * p.n_splits;
+
+    if (warp == 0) {
+        // ===================== TMA: the query tile of an item once, then its dictionary tiles
+        if (elect_one_sync()) {
+            unsigned it = 0, qit = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++qit) {
+                const int split = item / p.n_qtiles, qt = item - split * p.n_qtiles;
+                const long long tile0 = (long long)split * p.tiles_per_split;
+                long long tile1 = tile0 + p.tiles_per_split;
+                if (tile1 > total_tiles) tile1 = total_tiles;
+                mbar_wait_bounded(q_empty, (qit & 1u) ^ 1u);
+                mbar_expect_tx(q_full, kScrQB);
+                tma_load_2d(smem_q, &map_q, 0, qt * kScrM, q_full);
+                for (long long t = tile0; t < tile1; ++t, ++it) {
+                    const int s = it % kScrStages;
+                    mbar_wait_bounded(&d_empty[s], ((it / kScrStages) & 1u) ^ 1u);
+                    mbar_expect_tx(&d_full[s], kScrTileB);
+                    tma_load_2d(smem_d + s * kScrTileB, &map_d, 0, (int)(t * kScrN), &d_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA: s~ = q_hi.d_hi + q_hi.d_lo + q_lo.d_hi, one accumulator per dictionary tile
+        if (elect_one_sync()) {
+            constexpr uint32_t idesc = umma_idesc_f16(kScrN);
+            unsigned it = 0, qit = 0, tj = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++qit) {
+                const int split = item / p.n_qtiles;
+                const long long tile0 = (long long)split * p.tiles_per_split;
+                long long tile1 = tile0 + p.tiles_per_split;
+                if (tile1 > total_tiles) tile1 = total_tiles;
+                mbar_wait_bounded(q_full, qit & 1u);
+                tc_fence_after();
+                const uint32_t qa = smem_u32(smem_q);
+                for (long long t = tile0; t < tile1; ++t, ++it, ++tj) {
+                    const int s = it % kScrStages, buf = tj & 1;
+                    mbar_wait_bounded(&tempty[buf], ((tj >> 1) & 1u) ^ 1u);
+                    mbar_wait_bounded(&d_full[s], (it / kScrStages) & 1u);
+                    tc_fence_after();
+                    const uint32_t db = smem_u32(smem_d + s * kScrTileB);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kScrN);
+                    umma_f16(d_tmem, umma_smem_desc<kScrRowB>(qa), umma_smem_desc<kScrRowB>(db), idesc, 0u);            // hi.hi
+                    umma_f16(d_tmem, umma_smem_desc<kScrRowB>(qa), umma_smem_desc<kScrRowB>(db + 32), idesc, 1u);       // hi.lo
+                    umma_f16(d_tmem, umma_smem_desc<kScrRowB>(qa + 32), umma_smem_desc<kScrRowB>(db), idesc, 1u);       // lo.hi
+                    umma_commit(&d_empty[s]);
+                    umma_commit(&tfull[buf]);
+                }
+                umma_commit(q_empty);  // the query tile may be replaced once this item's MMAs have read it
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: threshold filter, one thread = one query x one column half
+        const int quarter = warp & 3, half = (warp - 4) >> 2;
+        const int m = quarter * 32 + lane;
+        unsigned tj = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int split = item / p.n_qtiles, qt = item - split * p.n_qtiles;
+            const long long tile0 = (long long)split * p.tiles_per_split;
+            long long tile1 = tile0 + p.tiles_per_split;
+            if (tile1 > total_tiles) tile1 = total_tiles;
+            const bool live = (long long)qt * kScrM + m < p.Q;
+            const long long slot = ((long long)item * 2 + half) * kScrM + m;
+            float *cs = p.cand_s + slot * kScrCap;
+            int *ci = p.cand_i + slot * kScrCap;
+            int cnt = 0;
+            // k prefix rows have exact dots >= tau0, so S_k >= tau0; a row with s~ < tau0 - EPS has s < tau0
+            float thr = live ? p.tau0[((long long)qt * kScrM + m) * p.k + (p.k - 1)] - kScrEps : INFINITY;
+            for (long long t = tile0; t < tile1; ++t, ++tj) {
+                const int buf = tj & 1;
+                mbar_wait_bounded(&tfull[buf], (tj >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kScrN + half * 128);
+                const long long row_base = t * kScrN + half * 128;
+                // survivors of one 32-column chunk (rare): append, compact the buffer when it fills up
+                auto scan = [&](const float (&v)[32], int c0) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const long long row = row_base + c0 + i;
+                        if (v[i] >= thr && row < p.N) {   // rows past the end are TMA zero fill
+                            cs[cnt] = v[i];
+                            ci[cnt] = (int)row;
+                            if (++cnt == kScrCap) {
+                                const float kth = kth_largest(cs, kScrCap, p.k);
+                                thr = kth - 2.0f * kScrEps;
+                                int w = 0;
+                                for (int r = 0; r < kScrCap; ++r) {
+                                    const float sv = cs[r];
+                                    const int iv = ci[r];
+                                    if (sv >= thr) {
+                                        cs[w] = sv;
+                                        ci[w] = iv;
+                                        ++w;
+                                    }
+                                }
+                                cnt = w;
+                                if (cnt == kScrCap) {
+                                    // more than CAP rows within 2 EPS of the k-th best (massive duplication): the
+                                    // screen cannot narrow this query down; the re-rank scans the range exactly
+                                    cnt = -1;
+                                    thr = INFINITY;
+                                }
+                            }
+                        }
+                    }
+                };
+                auto chunk_max = [](const float (&v)[32]) {
+                    float a = fmaxf(v[0], v[1]), b = fmaxf(v[2], v[3]), c = fmaxf(v[4], v[5]), d = fmaxf(v[6], v[7]);
+#pragma unroll
+                    for (int i = 8; i < 32; i += 4) {
+                        a = fmaxf(a, v[i]);
+                        b = fmaxf(b, v[i + 1]);
+                        c = fmaxf(c, v[i + 2]);
+                        d = fmaxf(d, v[i + 3]);
+                    }
+                    return fmaxf(fmaxf(a, b), fmaxf(c, d));
+                };
+                // one 32-column chunk per round trip (two loads in flight measured slower: 59 vs 39 ms at 1M x 65536)
+#pragma unroll 1
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(t_row + c0, v);
+                    tmem_ld_wait();
+                    if (live && chunk_max(v) >= thr) scan(v, c0);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]);
+            }
+            p.cand_n[slot] = cnt;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace ebsd

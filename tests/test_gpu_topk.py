@@ -138,3 +138,36 @@ def test_full_size_properties_1m_rows():
     odot, oidx = T.topk(dn, qh[:48].cpu().numpy(), 10, nthreads=8)
     np.testing.assert_array_equal(idx[:48].cpu().numpy(), oidx)
     np.testing.assert_array_equal(dot[:48].cpu().numpy(), odot)
+
+
+def test_tensor_core_screen_equals_exact_kernel_incl_overflow_fallback():
+    """for large dictionaries ebsd_topk screens with tensor cores and re-ranks the survivors with the
+    canonical arithmetic.  Its lists must equal the CUDA-core kernel's bit for bit -- also for queries whose k-th best
+    dot is shared by hundreds of duplicate rows (survivor buffers overflow -> exact scan of the range) -- and the
+    sampled oracle check pins both to the restatement."""
+    import os
+    g = torch.Generator(device="cuda").manual_seed(77)
+    n, q = 420_000, 1500
+    d = torch.randn((n, 16), generator=g, device="cuda")
+    d[100_000:100_700] = d[5]                     # 700 exact copies of row 5
+    d[300_000:300_040] = d[6] * 3.0               # 40 rescaled copies of row 6 (identical after normalisation)
+    import ebsd_vae_b200 as E
+    db = E.LatentVectorDatabase()
+    db.add_vectors(d, torch.zeros((n, 3), dtype=torch.float64, device="cuda"))
+    qs = d[torch.randint(0, n, (q,), generator=g, device="cuda")] + 0.03 * torch.randn((q, 16), generator=g, device="cuda")
+    qs[0] = d[5]
+    qs[1] = d[6]
+    qh = db._prepare_queries(qs)
+    dot_s, idx_s, _ = db.search_device(qh, 10)                       # screen path (N >= 400k, Q >= 1024)
+    os.environ["EBSD_TOPK_SCREEN_OFF_FOR_TEST"] = "1"
+    try:
+        dot_e, idx_e, _ = db.search_device(qh[:1000].contiguous(), 10)   # Q < 1024 -> CUDA-core kernel
+    finally:
+        del os.environ["EBSD_TOPK_SCREEN_OFF_FOR_TEST"]
+    assert torch.equal(idx_s[:1000], idx_e) and torch.equal(dot_s[:1000], dot_e)
+    assert idx_s[0].tolist() == [5] + list(range(100_000, 100_009))  # ties: lowest rows win
+    assert idx_s[1].tolist()[:1] == [6] and set(idx_s[1].tolist()[1:]) <= set(range(300_000, 300_040))
+    dn = db._latents[:n].cpu().numpy()
+    odot, oidx = T.topk(dn, qh[:24].cpu().numpy(), 10, nthreads=8)
+    np.testing.assert_array_equal(idx_s[:24].cpu().numpy(), oidx)
+    np.testing.assert_array_equal(dot_s[:24].cpu().numpy(), odot)
