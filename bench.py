@@ -425,6 +425,22 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
         "consensus_queries_per_s": N_QUERY_PER_GPU / (cons_ms * 1e-3),
     }
 
+    # search quality next to the numbers: the reference's Chroma/HNSW index is approximate, this search is exact.
+    # chromadb / hnswlib are not installable in this image (no network), so their recall cannot be measured here;
+    # what can be stated is the agreement of the exact fp32 lists with a float64 brute force on a query sample.
+    n_s = 256
+    d64 = db._latents[: db.get_count()].double()
+    ref64 = torch.topk(qh[:n_s].double() @ d64.T, TOP_N, dim=1).indices + db.index_base
+    hit = (idx_loc[:n_s].unsqueeze(2) == ref64.unsqueeze(1)).any(dim=2).float().mean().item()
+    try:
+        import chromadb  # noqa: F401
+        chroma_note = "chromadb importable but not exercised by bench.py"
+    except Exception:  # noqa: BLE001
+        chroma_note = "unavailable: chromadb / chroma-hnswlib are not installed in this image (approximate HNSW index)"
+    search_quality = {"exact_fp32_vs_float64_recall_at_%d" % TOP_N: hit, "sample_queries": n_s,
+                      "reference_chroma_hnsw_recall": chroma_note}
+    del d64, ref64
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -440,6 +456,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
             "clocks": clocks.summary(),
             "roofline": roofline,
             "stages": stages,
+            "search_quality": search_quality,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
