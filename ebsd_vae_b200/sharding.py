@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 from . import _native
-from .vector_db import LatentVectorDatabase, LatentVectorDatabaseConfig, OrientationResultBatch
+from .vector_db import _to_host, LatentVectorDatabase, LatentVectorDatabaseConfig, OrientationResultBatch
 
 
 def all_gather_counts(n: int, group=None, device="cpu") -> list[int]:
@@ -132,8 +132,8 @@ class ShardedLatentVectorDatabase(LatentVectorDatabase):
             raise IndexError("top_n candidates fewer than max_iterations (chroma_db.py:302-303)")
         _, mean_e, success, mask, _, cand = self.consensus_device(idx, orientation_threshold, min_required_matches,
                                                                   max_iterations)
+        qv, idx_h, dist_h, cand_h, succ_h, mean_h, mask_h = _to_host(q_in.detach(), idx, dist_, cand, success, mean_e, mask)
         return OrientationResultBatch(
-            query_vectors=q_in.detach().cpu().numpy(), indices=idx.cpu().numpy(), distances=dist_.cpu().numpy(),
-            candidate_orientations=cand.cpu().numpy(), success=success.cpu().numpy().astype(bool),
-            mean_orientations=mean_e.cpu().numpy(), similar_masks=mask.cpu().numpy().astype(np.uint64),
+            query_vectors=qv, indices=idx_h, distances=dist_h, candidate_orientations=cand_h,
+            success=succ_h.astype(bool), mean_orientations=mean_h, similar_masks=mask_h.astype(np.uint64),
             faiss_mode=self.config.mode == "faiss")

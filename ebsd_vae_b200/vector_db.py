@@ -119,6 +119,24 @@ class OrientationResultBatch(Sequence):
         )
 
 
+def _to_host(*tensors):
+    """Device tensors -> numpy arrays with ONE stream synchronisation (pinned staging from torch's caching host
+    allocator, non-blocking copies).  Host tensors pass through."""
+    staged = []
+    dev = None
+    for t in tensors:
+        if t.device.type == "cuda":
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            dev = t.device
+            staged.append(h)
+        else:
+            staged.append(t)
+    if dev is not None:
+        torch.cuda.current_stream(dev).synchronize()
+    return tuple(h.numpy() for h in staged)  # views: the (pinned) staging lives as long as the arrays do
+
+
 class LatentVectorDatabase:
     """Exact-search latent dictionary resident in GPU memory."""
 
@@ -411,14 +429,16 @@ class LatentVectorDatabase:
             raise IndexError(f"index {min(n_avail, k)} is out of bounds for axis 0 with size {min(n_avail, k)}")
         _, mean_e, success, mask, _, cand = self.consensus_device(idx, orientation_threshold, min_required_matches,
                                                                   max_iterations)
+        # one synchronisation for all result arrays: asynchronous copies into pinned staging, then a single wait
+        qv, idx_h, dist_h, cand_h, succ_h, mean_h, mask_h = _to_host(q_in.detach(), idx, dist, cand, success, mean_e, mask)
         return OrientationResultBatch(
-            query_vectors=q_in.detach().cpu().numpy(),
-            indices=idx.cpu().numpy(),
-            distances=dist.cpu().numpy(),
-            candidate_orientations=cand.cpu().numpy(),
-            success=success.cpu().numpy().astype(bool),
-            mean_orientations=mean_e.cpu().numpy(),
-            similar_masks=mask.cpu().numpy().astype(np.uint64),
+            query_vectors=qv,
+            indices=idx_h,
+            distances=dist_h,
+            candidate_orientations=cand_h,
+            success=succ_h.astype(bool),
+            mean_orientations=mean_h,
+            similar_masks=mask_h.astype(np.uint64),
             faiss_mode=self.config.mode == "faiss",
         )
 
