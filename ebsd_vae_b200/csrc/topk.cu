@@ -397,8 +397,8 @@ __global__ void __launch_bounds__(256) topk_rerank_kernel(const float *__restric
     int e_idx = kIdxEmpty;
     for (int split = 0; split < p.n_splits; ++split) {
         const int item = split * p.n_qtiles + qt;
-        for (int half = 0; half < 2; ++half) {
-            const long long slot = ((long long)item * 2 + half) * kScrM + m;
+        for (int half = 0; half < kScrGroups; ++half) {
+            const long long slot = ((long long)item * kScrGroups + half) * kScrM + m;
             const int n = p.cand_n[slot];
             if (n >= 0) {
                 for (int base = 0; base < n; base += 32) {
@@ -418,15 +418,15 @@ __global__ void __launch_bounds__(256) topk_rerank_kernel(const float *__restric
                 long long tile1 = tile0 + p.tiles_per_split;
                 if (tile1 > total_tiles) tile1 = total_tiles;
                 for (long long t = tile0; t < tile1; ++t)
-                    for (int c0 = 0; c0 < 128; c0 += 32) {
-                        const long long row = t * kScrN + half * 128 + c0 + lane;
+                    for (int c0 = 0; c0 < kScrGroupCols; c0 += 32) {
+                        const long long row = t * kScrN + half * kScrGroupCols + c0 + lane;
                         const float d = row < p.N ? canonical_dot(qv, dict + row * kD) : -INFINITY;
                         const float kth = __shfl_sync(0xffffffffu, e_dot, p.k - 1);
                         unsigned mask = __ballot_sync(0xffffffffu, row < p.N && d >= kth);
                         while (mask) {
                             const int src = __ffs(mask) - 1;
                             mask &= mask - 1;
-                            warp_insert<int>(e_dot, e_idx, __shfl_sync(0xffffffffu, d, src), (int)(t * kScrN + half * 128 + c0 + src), lane);
+                            warp_insert<int>(e_dot, e_idx, __shfl_sync(0xffffffffu, d, src), (int)(t * kScrN + half * kScrGroupCols + c0 + src), lane);
                         }
                     }
             }
@@ -501,8 +501,10 @@ struct ScreenPlan {
 };
 
 // Rows of the seeding search.  With tau0 the k-th best of N/8 rows a query keeps about 8k survivors over the whole
-// dictionary (k / n0 per row), spread over its buffers: the CAP-entry buffers practically never fill, so the costly
-// in-place compaction stays an exception; the seeding search itself costs 1/8 of a CUDA-core search.
+// dictionary (k / n0 per row), spread over its (splits x column groups) buffers: the CAP-entry buffers practically
+// never fill, so the costly in-place compaction stays an exception; the seeding search itself costs 1/8 of a
+// CUDA-core search.  (N/16 measured slower: 41.7 vs 34.6 ms at 1M x 65536 -- twice the survivors, and every survivor
+// makes its whole warp walk the 32-column chunk.)
 static long long screen_prefix_rows(long long N) {
     long long n0 = N / 8;
     if (n0 < 4096) n0 = 4096;
@@ -531,7 +533,7 @@ static ScreenPlan make_screen_plan(long long N, long long Q, int sms) {
     const long long total_tiles = (N + kScrN - 1) / kScrN;
     long long s = (2ll * sms + pl.n_qtiles - 1) / pl.n_qtiles;          // aim at two waves of work items
     if (s > total_tiles / 8) s = total_tiles / 8;                         // at least 8 tiles per split
-    if (s > 2048 / pl.n_qtiles) s = 2048 / pl.n_qtiles;                   // bounds the candidate buffers (~128 KiB/item)
+    if (s > 1024 / pl.n_qtiles) s = 1024 / pl.n_qtiles;                   // bounds the candidate buffers (~256 KiB/item)
     if (s < 1) s = 1;
     pl.tiles_per_split = (int)((total_tiles + s - 1) / s);
     pl.n_splits = (int)((total_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split);
@@ -542,7 +544,7 @@ static ScreenPlan make_screen_plan(long long N, long long Q, int sms) {
         off += (bytes + 1023) & ~(size_t)1023;
         return r;
     };
-    const size_t slots = (size_t)pl.items * 2 * kScrM;
+    const size_t slots = (size_t)pl.items * kScrGroups * kScrM;
     pl.off_dpairs = take((size_t)total_tiles * kScrN * kScrRowB);      // padded to whole tiles
     pl.off_qpairs = take((size_t)pl.n_qtiles * kScrM * kScrRowB);
     pl.off_cs = take(slots * kScrCap * sizeof(float));

@@ -36,8 +36,10 @@ constexpr int kScrTileB = kScrN * kScrRowB;   // 16 KiB
 constexpr int kScrQB = kScrM * kScrRowB;      // 8 KiB
 constexpr int kScrStages = 6;
 constexpr int kScrCap = 64;          // survivors a buffer holds before it is compacted (> EBSD_MAX_TOPK)
+constexpr int kScrGroups = 4;        // column groups of a tile (epilogue warps per TMEM lane quarter)
+constexpr int kScrGroupCols = kScrN / kScrGroups;
 constexpr float kScrEps = 1e-5f;
-constexpr int kScrThreads = 384;     // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4..11 epilogue (lane quarter x column half)
+constexpr int kScrThreads = 128 + 128 * kScrGroups;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4.. epilogue (lane quarter x column group)
 constexpr int kScrSmem = 1024 + kScrStages * kScrTileB + kScrQB + 256;
 
 struct ScreenParams {
@@ -45,9 +47,9 @@ struct ScreenParams {
     int k;
     int n_qtiles, n_splits, tiles_per_split;
     const float *tau0;  // [Q][k]: exact top-k dots of a dictionary prefix (column k-1 seeds the threshold)
-    float *cand_s;      // [items][2][128][CAP] approximate dots
-    int *cand_i;        // [items][2][128][CAP] shard-local rows
-    int *cand_n;        // [items][2][128]      entries used
+    float *cand_s;      // [items][groups][128][CAP] approximate dots
+    int *cand_i;        // [items][groups][128][CAP] shard-local rows
+    int *cand_n;        // [items][groups][128]      entries used
 };
 
 // fp32 rows [n,16] -> fp16 pairs [n][hi(16) | lo(16)]
@@ -111,7 +113,7 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
         mbar_init(q_empty, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], 8);
+            mbar_init(&tempty[b], 4 * kScrGroups);
         }
         mbar_fence_init();
         tma_prefetch_desc(&map_d);
@@ -177,7 +179,7 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
         }
     } else if (warp >= 4) {
         // ===================== epilogue: threshold filter, one thread = one query x one column half
-        const int quarter = warp & 3, half = (warp - 4) >> 2;
+        const int quarter = warp & 3, half = (warp - 4) >> 2;   // `half` = column group of this warp
         const int m = quarter * 32 + lane;
         unsigned tj = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -186,7 +188,7 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
             long long tile1 = tile0 + p.tiles_per_split;
             if (tile1 > total_tiles) tile1 = total_tiles;
             const bool live = (long long)qt * kScrM + m < p.Q;
-            const long long slot = ((long long)item * 2 + half) * kScrM + m;
+            const long long slot = ((long long)item * kScrGroups + half) * kScrM + m;
             float *cs = p.cand_s + slot * kScrCap;
             int *ci = p.cand_i + slot * kScrCap;
             int cnt = 0;
@@ -196,8 +198,8 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
                 const int buf = tj & 1;
                 mbar_wait_bounded(&tfull[buf], (tj >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kScrN + half * 128);
-                const long long row_base = t * kScrN + half * 128;
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kScrN + half * kScrGroupCols);
+                const long long row_base = t * kScrN + half * kScrGroupCols;
                 // survivors of one 32-column chunk (rare): append, compact the buffer when it fills up
                 auto scan = [&](const float (&v)[32], int c0) {
 #pragma unroll
@@ -243,7 +245,7 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
                 };
                 // one 32-column chunk per round trip (two loads in flight measured slower: 59 vs 39 ms at 1M x 65536)
 #pragma unroll 1
-                for (int c0 = 0; c0 < 128; c0 += 32) {
+                for (int c0 = 0; c0 < kScrGroupCols; c0 += 32) {
                     float v[32];
                     tmem_ld32(t_row + c0, v);
                     tmem_ld_wait();
