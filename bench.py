@@ -40,6 +40,7 @@ METRIC = "patterns indexed/s (encode+top-10+consensus)"
 UNIT = "patterns/s"
 N_DICT_PER_GPU = 100_000
 N_QUERY_PER_GPU = 10_000
+CUSTOM_WORKLOAD = False   # --rows-per-gpu / --queries-per-gpu given: not the headline configuration
 TOP_N = 10
 THRESHOLD = 3.0
 MIN_REQUIRED = 5          # exercises the symmetry + mean path (the reference default 18 > top_n always fails)
@@ -242,6 +243,10 @@ def run_reference(args, rank: int, world: int):
 
 
 def workload_name(world: int) -> str:
+    if CUSTOM_WORKLOAD:
+        return (f"custom (not the headline): {N_DICT_PER_GPU * world}-row dictionary row-sharded over {world} GPU(s), "
+                f"{N_QUERY_PER_GPU * world} query patterns split data-parallel"
+                + ("; = BASELINE configs[3] (10M-entry dictionary on 8 B200)" if N_DICT_PER_GPU * world == 10_000_000 else ""))
     if world == 1:
         return "configs[1]: synthetic 100k-orientation dictionary, 128x128 patterns, latent dim 16, 10k-query batch"
     return (f"configs[1] per GPU x {world} (weak): {N_DICT_PER_GPU * world}-row dictionary row-sharded over {world} "
@@ -470,7 +475,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rows-per-gpu", type=int, default=None,
+                    help="dictionary rows per GPU (default 100000 = BASELINE configs[1]; 1250000 x 8 GPUs = the 10M-row "
+                         "configs[3]); a non-default value is named in config.workload")
+    ap.add_argument("--queries-per-gpu", type=int, default=None, help="query patterns per GPU (default 10000)")
     args = ap.parse_args()
+    global N_DICT_PER_GPU, N_QUERY_PER_GPU, CUSTOM_WORKLOAD
+    if args.rows_per_gpu:
+        N_DICT_PER_GPU = args.rows_per_gpu
+        CUSTOM_WORKLOAD = True
+    if args.queries_per_gpu:
+        N_QUERY_PER_GPU = args.queries_per_gpu
+        CUSTOM_WORKLOAD = True
     if args.impl == "b200" and args.warmup < 3:
         args.warmup = 3  # timing rule: at least 3 warm-up steps
 
