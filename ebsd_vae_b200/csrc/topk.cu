@@ -381,10 +381,11 @@ __device__ __forceinline__ float canonical_dot(const float4 (&q)[4], const float
     return a;
 }
 
+// init_from_out: the output arrays already hold the exact top-k of the rows below the pass (global indices); they
+// seed the list, so the result is the top-k over both ranges.
 __global__ void __launch_bounds__(256) topk_rerank_kernel(const float *__restrict__ dict, const float *__restrict__ queries,
-                                                          const ScreenParams p, long long index_base,
-                                                          float *__restrict__ out_dot, long long *__restrict__ out_idx,
-                                                          float *__restrict__ out_dist) {
+                                                          const ScreenParams p, long long index_base, int init_from_out,
+                                                          float *out_dot, long long *out_idx, float *out_dist) {
     const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (q >= p.Q) return;
@@ -392,9 +393,17 @@ __global__ void __launch_bounds__(256) topk_rerank_kernel(const float *__restric
 #pragma unroll
     for (int c = 0; c < 4; ++c) qv[c] = __ldg((const float4 *)(queries + q * kD) + c);
     const int qt = (int)(q / kScrM), m = (int)(q % kScrM);
-    const long long total_tiles = (p.N + kScrN - 1) / kScrN;
+    const long long total_tiles = p.tile_end;
     float e_dot = -INFINITY;
     int e_idx = kIdxEmpty;
+    if (init_from_out && lane < p.k) {   // a sorted list: lane l takes entry l
+        const long long gi = out_idx[q * p.k + lane];
+        if (gi >= 0) {
+            e_dot = out_dot[q * p.k + lane];
+            e_idx = (int)(gi - index_base);
+        }
+    }
+    __syncwarp();
     for (int split = 0; split < p.n_splits; ++split) {
         const int item = split * p.n_qtiles + qt;
         for (int half = 0; half < kScrGroups; ++half) {
@@ -414,7 +423,7 @@ __global__ void __launch_bounds__(256) topk_rerank_kernel(const float *__restric
                         warp_insert<int>(e_dot, e_idx, __shfl_sync(0xffffffffu, d, j2), __shfl_sync(0xffffffffu, row, j2), lane);
                 }
             } else {
-                const long long tile0 = (long long)split * p.tiles_per_split;
+                const long long tile0 = p.tile_begin + (long long)split * p.tiles_per_split;
                 long long tile1 = tile0 + p.tiles_per_split;
                 if (tile1 > total_tiles) tile1 = total_tiles;
                 for (long long t = tile0; t < tile1; ++t)
@@ -506,7 +515,7 @@ struct ScreenPlan {
 // CUDA-core search.  (N/16 measured slower: 41.7 vs 34.6 ms at 1M x 65536 -- twice the survivors, and every survivor
 // makes its whole warp walk the 32-column chunk.)
 static long long screen_prefix_rows(long long N) {
-    long long n0 = N / 8;
+    long long n0 = N / 8;   // called with N = the rows of stage B (N/8 of the dictionary): n0 = N/64
     if (n0 < 4096) n0 = 4096;
     return n0 < N ? n0 : N;
 }
@@ -550,7 +559,9 @@ static ScreenPlan make_screen_plan(long long N, long long Q, int sms) {
     pl.off_cs = take(slots * kScrCap * sizeof(float));
     pl.off_ci = take(slots * kScrCap * sizeof(int));
     pl.off_cn = take(slots * sizeof(int));
-    const TopkPlan ex = make_plan(screen_prefix_rows(N), Q, sms);   // partial lists of the seeding search
+    // partial lists of the stage-A seeding search (the CUDA-core kernel over N/64 rows, see run_screen)
+    const long long n1_rows = ((N / 8 + kScrN - 1) / kScrN) * kScrN;
+    const TopkPlan ex = make_plan(screen_prefix_rows(n1_rows), Q, sms);
     pl.off_parts = take(ex.n_splits > 1 ? (size_t)ex.n_splits * (size_t)Q * 32 * sizeof(Entry) : 1024);
     pl.bytes = off + 1024;
     return pl;
@@ -657,35 +668,51 @@ static int run_screen(const float *dict, long long N, long long index_base, cons
     int rc;
     if ((rc = make_pairs_map(&map_d, dpairs, drows, kScrN))) return rc;
     if ((rc = make_pairs_map(&map_q, qpairs, qrows, kScrM))) return rc;
-    // Seed every query's threshold with its exact k-th best dot over a PREFIX of the dictionary (CUDA-core kernel,
-    // 1/8 of the rows): k rows are then known to have s >= tau0, so rows with s~ < tau0 - EPS can be dropped from
-    // the first tile on and the survivor buffers almost never fill up.  out_dot is reused as scratch for tau0.
-    const long long n0 = screen_prefix_rows(N);
-    if ((rc = run_exact(dict, n0, index_base, queries, Q, k, out_dot, out_idx, nullptr, ws + pl.off_parts, sms, st))) return rc;
-    ScreenParams p;
-    p.Q = Q;
-    p.N = N;
-    p.k = k;
-    p.n_qtiles = pl.n_qtiles;
-    p.n_splits = pl.n_splits;
-    p.tiles_per_split = pl.tiles_per_split;
-    p.tau0 = out_dot;
-    p.cand_s = (float *)(ws + pl.off_cs);
-    p.cand_i = (int *)(ws + pl.off_ci);
-    p.cand_n = (int *)(ws + pl.off_cn);
+    // Thresholds are seeded in stages, each giving k rows whose exact dots bound the final k-th best from below:
+    //   A  CUDA-core search of the first n0 = N/64 rows                    -> exact top-k of [0, n0)
+    //   B  screen + re-rank of the first n1 = N/8 rows, thr from A         -> exact top-k of [0, n1)   (~8k survivors)
+    //   C  screen of the remaining rows [n1, N), thr from B; the re-rank starts from B's list -> top-k of [0, N)
+    // out_dot / out_idx carry the running exact lists between the stages (each kernel reads them before the next
+    // one overwrites them: same stream).
     static bool configured = false;
     if (!configured) {
         EBSD_CUDA_TRY(cudaFuncSetAttribute(topk_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScrSmem));
         configured = true;
     }
-    const int grid = pl.items < sms ? pl.items : sms;
-    topk_screen_kernel<<<grid, kScrThreads, kScrSmem, st>>>(map_d, map_q, p);
-    EBSD_LAUNCH_CHECK();
-    const int wpb = 8;
-    topk_rerank_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, st>>>(dict, queries, p, index_base, out_dot, out_idx,
-                                                                          out_dist);
-    EBSD_LAUNCH_CHECK();
-    return EBSD_OK;
+    const long long n1_tiles = ((N / 8 + kScrN - 1) / kScrN);
+    const long long n0 = screen_prefix_rows(n1_tiles * kScrN);   // N/64, at least 4096
+    if ((rc = run_exact(dict, n0, index_base, queries, Q, k, out_dot, out_idx, nullptr, ws + pl.off_parts, sms, st))) return rc;
+    auto pass = [&](long long tile_begin, long long tile_end, int init_from_out) -> int {
+        ScreenParams p;
+        p.Q = Q;
+        p.N = N;
+        p.k = k;
+        p.n_qtiles = pl.n_qtiles;
+        p.tile_begin = tile_begin;
+        p.tile_end = tile_end;
+        // split the pass over the same number of work items per query tile as the plan allows
+        long long s = pl.n_splits;
+        const long long tiles = tile_end - tile_begin;
+        if (s > tiles / 8) s = tiles / 8;
+        if (s < 1) s = 1;
+        p.tiles_per_split = (int)((tiles + s - 1) / s);
+        p.n_splits = (int)((tiles + p.tiles_per_split - 1) / p.tiles_per_split);
+        p.tau0 = out_dot;
+        p.cand_s = (float *)(ws + pl.off_cs);
+        p.cand_i = (int *)(ws + pl.off_ci);
+        p.cand_n = (int *)(ws + pl.off_cn);
+        const int items = p.n_qtiles * p.n_splits;
+        const int grid = items < sms ? items : sms;
+        topk_screen_kernel<<<grid, kScrThreads, kScrSmem, st>>>(map_d, map_q, p);
+        EBSD_LAUNCH_CHECK();
+        const int wpb = 8;
+        topk_rerank_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, st>>>(dict, queries, p, index_base, init_from_out,
+                                                                              out_dot, out_idx, out_dist);
+        EBSD_LAUNCH_CHECK();
+        return EBSD_OK;
+    };
+    if ((rc = pass(0, n1_tiles, 0))) return rc;
+    return pass(n1_tiles, total_tiles, 1);
 }
 
 }  // namespace ebsd

@@ -46,6 +46,7 @@ struct ScreenParams {
     long long Q, N;
     int k;
     int n_qtiles, n_splits, tiles_per_split;
+    long long tile_begin, tile_end;   // dictionary tiles (256 rows each) this pass covers
     const float *tau0;  // [Q][k]: exact top-k dots of a dictionary prefix (column k-1 seeds the threshold)
     float *cand_s;      // [items][groups][128][CAP] approximate dots
     int *cand_i;        // [items][groups][128][CAP] shard-local rows
@@ -125,7 +126,7 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const long long total_tiles = (p.N + kScrN - 1) / kScrN;
+    const long long total_tiles = p.tile_end;
     const int n_items = p.n_qtiles * p.n_splits;
 
     if (warp == 0) {
@@ -134,7 +135,7 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
             unsigned it = 0, qit = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++qit) {
                 const int split = item / p.n_qtiles, qt = item - split * p.n_qtiles;
-                const long long tile0 = (long long)split * p.tiles_per_split;
+                const long long tile0 = p.tile_begin + (long long)split * p.tiles_per_split;
                 long long tile1 = tile0 + p.tiles_per_split;
                 if (tile1 > total_tiles) tile1 = total_tiles;
                 mbar_wait_bounded(q_empty, (qit & 1u) ^ 1u);
@@ -155,7 +156,7 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
             unsigned it = 0, qit = 0, tj = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++qit) {
                 const int split = item / p.n_qtiles;
-                const long long tile0 = (long long)split * p.tiles_per_split;
+                const long long tile0 = p.tile_begin + (long long)split * p.tiles_per_split;
                 long long tile1 = tile0 + p.tiles_per_split;
                 if (tile1 > total_tiles) tile1 = total_tiles;
                 mbar_wait_bounded(q_full, qit & 1u);
@@ -184,7 +185,7 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
         unsigned tj = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int split = item / p.n_qtiles, qt = item - split * p.n_qtiles;
-            const long long tile0 = (long long)split * p.tiles_per_split;
+            const long long tile0 = p.tile_begin + (long long)split * p.tiles_per_split;
             long long tile1 = tile0 + p.tiles_per_split;
             if (tile1 > total_tiles) tile1 = total_tiles;
             const bool live = (long long)qt * kScrM + m < p.Q;
