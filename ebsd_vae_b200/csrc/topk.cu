@@ -520,6 +520,8 @@ static long long screen_prefix_rows(long long N) {
     return n0 < N ? n0 : N;
 }
 
+constexpr long long kScreenQueryChunk = 131072;   // queries per screen pass (bounds the survivor buffers at ~256 MiB)
+
 static bool screen_enabled() {
     static int on = -1;
     if (on < 0) {
@@ -737,7 +739,7 @@ int ebsd_normalize_rows(float *x, int64_t n, int d, void *stream) {
 
 size_t ebsd_topk_workspace_bytes(int64_t N, int64_t Q, int k) {
     if (N <= 0 || Q <= 0 || k <= 0) return 0;
-    if (screen_applies(N, Q, k)) return make_screen_plan(N, Q, sm_count()).bytes;
+    if (screen_applies(N, Q, k)) return make_screen_plan(N, Q < kScreenQueryChunk ? Q : kScreenQueryChunk, sm_count()).bytes;
     const TopkPlan pl = make_plan(N, Q, sm_count());
     return pl.n_splits > 1 ? (size_t)pl.n_splits * (size_t)Q * (size_t)k * sizeof(Entry) : 0;
 }
@@ -766,12 +768,19 @@ int ebsd_topk(const float *dict, int64_t N, int64_t index_base, const float *que
 
     const int sms = sm_count();
     if (screen_applies(N, Q, k)) {
-        const size_t need_s = make_screen_plan(N, Q, sms).bytes;
+        const size_t need_s = make_screen_plan(N, Q < kScreenQueryChunk ? Q : kScreenQueryChunk, sms).bytes;
         if (workspace == nullptr || workspace_bytes < need_s) {
             set_error("ebsd_topk: workspace too small (%zu < %zu)", workspace_bytes, need_s);
             return EBSD_ERR_WORKSPACE;
         }
-        return run_screen(dict, N, index_base, queries, Q, k, out_dot, (long long *)out_idx, out_dist, workspace, sms, st);
+        // very large query batches go through in chunks: the survivor buffers scale with the number of query tiles
+        for (long long q0 = 0; q0 < Q; q0 += kScreenQueryChunk) {
+            const long long qn = Q - q0 < kScreenQueryChunk ? Q - q0 : kScreenQueryChunk;
+            if ((rc = run_screen(dict, N, index_base, queries + q0 * kD, qn, k, out_dot + q0 * k, (long long *)out_idx + q0 * k,
+                                 out_dist ? out_dist + q0 * k : nullptr, workspace, sms, st)))
+                return rc;
+        }
+        return EBSD_OK;
     }
     const TopkPlan pl = make_plan(N, Q, sms);
     const size_t need = pl.n_splits > 1 ? (size_t)pl.n_splits * (size_t)Q * (size_t)k * sizeof(Entry) : 0;
