@@ -33,6 +33,11 @@ enum FusedSrc { SRC_U8 = 0, SRC_F32 = 1, SRC_RAW = 2 };
 // +4 % on the whole encoder against single CTAs (profiles/README.md).  A four-term variant of the pair (one B region,
 // N = 2*COUT for both planes) was tried first and lost: under tensor load the chip is power-limited and the extra
 // term costs more than the halved weight traffic saves.  0 = single CTAs (make EXTRA=-DEBSD_PAIR=0).
+// tiles per work item of the 128x128 front-end block: 4 (two window stages of 18 x 34 positions) or 2 (four stages of
+// 18 x 18: deeper producer -> MMA decoupling, 6 % more halo work -- measured slower, 1911 vs 1491 us per 1184 patterns)
+#ifndef EBSD_FRONT_NT
+#define EBSD_FRONT_NT 4
+#endif
 #ifndef EBSD_PAIR
 #define EBSD_PAIR 1
 #endif
@@ -59,7 +64,7 @@ struct FusedCfg {
     // all nine taps stay in shared memory when they fit next to two windows: the 32-channel blocks always, the
     // 64 -> 64 block only as a pair (108 KB per CTA) and with one tile per window
     static constexpr bool RESIDENT_B = 9 * NCHUNK * B_CTA <= (PAIR ? 112 : 80) * 1024;
-    static constexpr int NT = W >= 128 ? 4 : (W >= 64 ? ((RESIDENT_B && CIN == 64) ? 1 : 2) : 1);  // tiles per work item
+    static constexpr int NT = W >= 128 ? EBSD_FRONT_NT : (W >= 64 ? ((RESIDENT_B && CIN == 64) ? 1 : 2) : 1);  // tiles per work item
     static constexpr int TR = 16 / NI;                       // image rows per tile
     static constexpr int WIN_H = TR + 2;
     static constexpr int PITCH = NI == 1 ? 8 * NT + 2 : 10 * NI;
@@ -74,7 +79,8 @@ struct FusedCfg {
     // operand reads of the tensor core, which matters because the single-CTA blocks are shared-memory-bandwidth bound.
     static constexpr int CL = PAIR ? 2 : 1;                  // cluster size
     static constexpr int B_BOX_ROWS = PAIR ? COUT / 2 : 2 * COUT;  // rows of one weight TMA box
-    static constexpr int A_STAGES = 2;
+    static constexpr int A_STAGES = (W >= 128 && EBSD_FRONT_NT == 2) ? 4 : 2;
+    static constexpr int PATCH_W = 8 * NT + 4, PATCH_H = 20;   // FIRST: input pixels a window needs (conv0 + conv1 halos)
     // output staging for the TMA stores: per epilogue warp one [32 or 8 rows][128 B] box, 128B-swizzled
     static constexpr int WSTG = POOL ? 1024 : 4096;
     // COUT = 32 with several tiles per item (the front end): the epilogue walks 16-channel halves outside the tile
@@ -751,7 +757,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 for (int j = 0; j < 4; ++j)
                     wreg[tp][j] = make_float2(__ldg(p.w0 + tp * 32 + cg * 8 + 2 * j), __ldg(p.w0 + tp * 32 + cg * 8 + 2 * j + 1));
             // the 20 x 36 input pixels of a window (conv0 halo on top of the conv1 halo) are fetched one item ahead
-            constexpr int NPV = (20 * 36 + C::PRODUCERS - 1) / C::PRODUCERS;
+            constexpr int NPV = (C::PATCH_H * C::PATCH_W + C::PRODUCERS - 1) / C::PRODUCERS;
             uint32_t pv[NPV];  // raw pixel bits; converted when they are written to the patch, one item later
             auto load_patch = [&](int item) {
                 int n, y0, x0;
@@ -759,10 +765,10 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 #pragma unroll
                 for (int i = 0; i < NPV; ++i) {
                     const int idx = ptid + C::PRODUCERS * i;
-                    const int py = idx / 36, px = idx - py * 36;
+                    const int py = idx / C::PATCH_W, px = idx - py * C::PATCH_W;
                     const int gy = y0 - 2 + py, gx = x0 - 2 + px;
                     uint32_t v = 0u;
-                    if (idx < 20 * 36 && n < p.nimg && gy >= 0 && gy < 128 && gx >= 0 && gx < 128) {
+                    if (idx < C::PATCH_H * C::PATCH_W && n < p.nimg && gy >= 0 && gy < 128 && gx >= 0 && gx < 128) {
                         const long long off = ((long long)n * 128 + gy) * 128 + gx;
                         if (SRC == SRC_U8) v = __ldg((const uint8_t *)p.src + off);
                         else v = __float_as_uint(__ldg((const float *)p.src + off));
@@ -778,7 +784,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 named_bar_sync(1, C::PRODUCERS);
 #pragma unroll
                 for (int i = 0; i < NPV; ++i)
-                    if (ptid + C::PRODUCERS * i < 20 * 36) {
+                    if (ptid + C::PRODUCERS * i < C::PATCH_H * C::PATCH_W) {
                         // ToTensor: uint8 -> float32, true division by 255 (latice/data_module.py:31)
                         const float v = SRC == SRC_U8 ? (float)pv[i] / 255.0f : __uint_as_float(pv[i]);
                         sts32(patch_u32 + (ptid + C::PRODUCERS * i) * 4, __float_as_uint(v));
@@ -804,7 +810,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                             for (int dx = 0; dx < 3; ++dx) {
-                                const float v = lds32(patch_u32 + ((wy + dy) * 36 + wx + dx) * 4);
+                                const float v = lds32(patch_u32 + ((wy + dy) * C::PATCH_W + wx + dx) * 4);
                                 const float2 vv = make_float2(v, v);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) acc[j] = __ffma2_rn(vv, wreg[dy * 3 + dx][j], acc[j]);
