@@ -38,6 +38,14 @@ enum FusedSrc { SRC_U8 = 0, SRC_F32 = 1, SRC_RAW = 2 };
 #ifndef EBSD_FRONT_NT
 #define EBSD_FRONT_NT 4
 #endif
+// staging boxes per epilogue warp of the un-pooled blocks (4 KiB each): a warp waits for the TMA store issued NSB
+// blocks earlier to have read its box before it refills it
+#ifndef EBSD_NSB_RESIDENT
+#define EBSD_NSB_RESIDENT 2
+#endif
+#ifndef EBSD_NSB_STREAMED
+#define EBSD_NSB_STREAMED 1
+#endif
 #ifndef EBSD_PAIR
 #define EBSD_PAIR 1
 #endif
@@ -86,7 +94,7 @@ struct FusedCfg {
     // COUT = 32 with several tiles per item (the front end): the epilogue walks 16-channel halves outside the tile
     // loop so that the plane sums stay in registers across the NT tiles; every tile then needs its own box
     static constexpr bool ACCUM = COUT == 32 && NT > 1;
-    static constexpr int NSB = ACCUM ? NT : ((!POOL && RESIDENT_B) ? 2 : 1);  // staging boxes per warp
+    static constexpr int NSB = ACCUM ? NT : (!POOL ? (RESIDENT_B ? EBSD_NSB_RESIDENT : EBSD_NSB_STREAMED) : 1);  // staging boxes per warp
     static constexpr int STAGING = 4 * NSB * WSTG;
     static constexpr int EXTRA = 8192 + STAGING;             // barriers, tables, conv0 patch | staging
     static constexpr int B_FIT = (226 * 1024 - 1024 - EXTRA - A_STAGES * A_STAGE) / B_CTA;

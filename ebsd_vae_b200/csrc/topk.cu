@@ -4,18 +4,20 @@
 // and ChromaLatentVectorDatabase.query_similar (latice/index/chroma_db.py:231-259).
 //
 // Shape of the kernel
-//   * persistent CTAs (one per SM) walk work items (query tile, dictionary split);
+//   * persistent CTAs (two per SM with TQ = 4) walk work items (query tile, dictionary split);
 //   * one elected thread streams 128-row dictionary tiles (8 KiB) into a 4-stage shared-memory ring with TMA
 //     (cp.async.bulk.tensor.2d, SWIZZLE_64B so that the consumers' LDS.128 are bank-conflict free); it runs
-//     kStages-1 tiles ahead of the consumers and is itself lane 0 of warp 0 (a ninth warp would cost the
-//     other eight a third of their register budget);
+//     kStages-1 tiles ahead of the consumers and is itself lane 0 of warp 0;
 //   * 8 warps each own 2*TQ queries; a thread holds a TQ x 8 register tile of dot products,
 //     accumulated as fma chains in ascending j (bit-identical to the oracle);
-//   * selection: every dot is compared with the query's current k-th best (tau, in registers); the rare
-//     survivors go through a warp-private candidate buffer into a sorted per-query list (one entry per lane,
-//     ballot + shuffle insertion).  No CTA-wide synchronisation in the steady state.
-//   * ties: dot descending, then row index ascending -- rows arrive in ascending order and tau only lets
-//     strictly larger dots through once the list is full, which is exactly that rule.
+//   * selection: per lane and query the best of its 8 rows is compared with the query's current k-th best (tau, in
+//     registers); one vote skips the tile, one ballot per query slot finds the lanes with survivors, and only those
+//     pay a ballot per row; survivors are inserted into a sorted per-query list (one entry per lane, ballot +
+//     shuffle insertion).  No CTA-wide synchronisation in the steady state.
+//   * ties: dot descending, then row index ascending -- per query the rows are visited in ascending order and tau
+//     only lets strictly larger dots through once the list is full, which is exactly that rule.
+//   * large dictionaries (N >= 400k, Q >= 1024) go through the tensor-core screen of topk_screen.cuh first and only
+//     the survivors are re-ranked with this arithmetic (topk_rerank_kernel): same lists, bit for bit.
 #include <math.h>
 #include <stdlib.h>
 
@@ -31,7 +33,6 @@ constexpr int kStages = 4;
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kListLen = 32;                    // one entry per lane; k <= 32
-constexpr int kCandCap = 16;                    // survivors per query per 16-row sub-step
 constexpr int kIdxEmpty = 0x7fffffff;
 
 struct __align__(8) Entry {
@@ -87,10 +88,7 @@ struct Smem {
     static constexpr int off_dtile = 0;
     static constexpr int off_qtile = off_dtile + kStages * kTileBytes;
     static constexpr int off_list = off_qtile + QT * kD * 4;
-    static constexpr int off_cand = off_list + QT * kListLen * 8;
-    static constexpr int off_cnt = off_cand + QT * kCandCap * 8;
-    static constexpr int off_tau = off_cnt + QT * 4;
-    static constexpr int off_bar = off_tau + QT * 4;
+    static constexpr int off_bar = off_list + QT * kListLen * 8;
     static constexpr int bytes = off_bar + 2 * kStages * 8;
     static constexpr int alloc = bytes + 1024;  // slack for manual 1024-byte alignment
 };
@@ -106,9 +104,6 @@ topk_kernel(const __grid_constant__ CUtensorMap dict_map, const TopkParams p) {
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     float *qtile = (float *)(smem + S::off_qtile);
     Entry *lists = (Entry *)(smem + S::off_list);
-    Entry *cands = (Entry *)(smem + S::off_cand);
-    int *cnt = (int *)(smem + S::off_cnt);
-    float *tau_s = (float *)(smem + S::off_tau);
     uint64_t *full_bar = (uint64_t *)(smem + S::off_bar);
     uint64_t *empty_bar = full_bar + kStages;
 
@@ -153,10 +148,6 @@ topk_kernel(const __grid_constant__ CUtensorMap dict_map, const TopkParams p) {
             for (int v = tid; v < QT * kListLen; v += kWarps * 32) {
                 lists[v].dot = -INFINITY;
                 lists[v].idx = kIdxEmpty;
-            }
-            for (int v = tid; v < QT; v += kWarps * 32) {
-                cnt[v] = 0;
-                tau_s[v] = -INFINITY;
             }
         }
         __syncthreads();
