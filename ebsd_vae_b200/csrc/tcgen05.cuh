@@ -60,10 +60,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+#ifndef EBSD_WAIT_HINT_NS
+#define EBSD_WAIT_HINT_NS 20000u
+#endif
 // Bounded mbarrier wait: a mis-programmed pipeline must trap, not hang the GPU.
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait_hint(bar, parity, EBSD_WAIT_HINT_NS)) {
         if (clock64() - t0 > 4000000000ll) {  // ~2 s
             printf("ebsd encoder: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
             __trap();

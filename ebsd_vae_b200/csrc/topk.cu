@@ -526,7 +526,12 @@ static bool screen_enabled() {
 static bool screen_applies(long long N, long long Q, int k) {
     // measured (profiles/README.md): the screen is bound by draining the accumulators from TMEM (one fp32 per pair,
     // ~2 us per 128 x 256 tile) and wins over the CUDA-core kernel only for large dictionaries
-    return screen_enabled() && k < kScrCap / 2 && N >= 400000 && Q >= 1024 && N < 0x7fffff00ll;
+    static long long min_rows = -1;
+    if (min_rows < 0) {
+        const char *e = getenv("EBSD_TOPK_SCREEN_MIN_ROWS");   // A/B timing of the switch-over point
+        min_rows = (e && atoll(e) > 0) ? atoll(e) : 400000;
+    }
+    return screen_enabled() && k < kScrCap / 2 && N >= min_rows && Q >= 1024 && N < 0x7fffff00ll;
 }
 
 static ScreenPlan make_screen_plan(long long N, long long Q, int sms) {

@@ -35,7 +35,7 @@ constexpr int kScrRowB = 64;         // bytes per operand row: 16 fp16 hi | 16 f
 constexpr int kScrTileB = kScrN * kScrRowB;   // 16 KiB
 constexpr int kScrQB = kScrM * kScrRowB;      // 8 KiB
 constexpr int kScrStages = 6;
-constexpr int kScrCap = 64;          // survivors a buffer holds before it is compacted (> EBSD_MAX_TOPK)
+constexpr int kScrCap = 96;          // entries of a survivor buffer; compacted when fewer than 32 are free (CAP - 32 > EBSD_MAX_TOPK)
 constexpr int kScrGroups = 4;        // column groups of a tile (epilogue warps per TMEM lane quarter)
 constexpr int kScrGroupCols = kScrN / kScrGroups;
 constexpr float kScrEps = 1e-5f;
@@ -87,6 +87,31 @@ __device__ __noinline__ float kth_largest(const float *vals, int n, int k) {
         if (taken >= k || cnt == 0) return best;
         bound = best;
     }
+}
+
+// A survivor buffer is nearly full: raise the threshold to (k-th largest kept s~) - 2 EPS and drop what falls below it.
+// If that does not make room for another 32-column chunk, more than CAP - 32 rows lie within 2 EPS of the k-th best
+// (massive duplication): the screen cannot narrow this query down, cnt = -1 tells the re-rank to scan the range exactly.
+// Returns (new threshold, new count as int bits): by value, so that the caller's cnt / thr stay in registers.
+__device__ __noinline__ float2 screen_compact(float *cs, int *ci, int cnt, int k) {
+    const float kth = kth_largest(cs, cnt, k);
+    float thr = kth - 2.0f * kScrEps;
+    int w = 0;
+    for (int r = 0; r < cnt; ++r) {
+        const float sv = cs[r];
+        const int iv = ci[r];
+        if (sv >= thr) {
+            cs[w] = sv;
+            ci[w] = iv;
+            ++w;
+        }
+    }
+    cnt = w;
+    if (cnt > kScrCap - 32) {
+        cnt = -1;
+        thr = INFINITY;
+    }
+    return make_float2(thr, __int_as_float(cnt));
 }
 
 __global__ void __launch_bounds__(kScrThreads, 1)
@@ -201,35 +226,27 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kScrN + half * kScrGroupCols);
                 const long long row_base = t * kScrN + half * kScrGroupCols;
-                // survivors of one 32-column chunk (rare): append, compact the buffer when it fills up
+                // survivors of one 32-column chunk (rare).  The code is kept SMALL on purpose: the first version inlined
+                // the buffer compaction into each of the 32 unrolled steps (17k SASS instructions, far beyond the
+                // instruction cache), every entry cost ~2000 cycles of instruction fetch, and because a tile is only
+                // released when all 16 warps are done, nearly every tile paid for it (ncu: 57 % of the epilogue time
+                // waiting for the next accumulator, tools/tmem_rate.cu: the TMEM drain itself takes ~450 cycles per
+                // tile).  Now: room for a whole chunk is made up front (out of line), the steps are predicated appends.
                 auto scan = [&](const float (&v)[32], int c0) {
+                    if (cnt > kScrCap - 32) {
+                        const float2 r = screen_compact(cs, ci, cnt, p.k);
+                        thr = r.x;
+                        cnt = __float_as_int(r.y);
+                    }
+                    const long long row0 = row_base + c0;
+                    const long long left = p.N - row0;   // rows past the end are TMA zero fill
+                    const int nvalid = left < 32 ? (int)left : 32;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const long long row = row_base + c0 + i;
-                        if (v[i] >= thr && row < p.N) {   // rows past the end are TMA zero fill
+                        if (v[i] >= thr && i < nvalid) {
                             cs[cnt] = v[i];
-                            ci[cnt] = (int)row;
-                            if (++cnt == kScrCap) {
-                                const float kth = kth_largest(cs, kScrCap, p.k);
-                                thr = kth - 2.0f * kScrEps;
-                                int w = 0;
-                                for (int r = 0; r < kScrCap; ++r) {
-                                    const float sv = cs[r];
-                                    const int iv = ci[r];
-                                    if (sv >= thr) {
-                                        cs[w] = sv;
-                                        ci[w] = iv;
-                                        ++w;
-                                    }
-                                }
-                                cnt = w;
-                                if (cnt == kScrCap) {
-                                    // more than CAP rows within 2 EPS of the k-th best (massive duplication): the
-                                    // screen cannot narrow this query down; the re-rank scans the range exactly
-                                    cnt = -1;
-                                    thr = INFINITY;
-                                }
-                            }
+                            ci[cnt] = (int)row0 + i;
+                            ++cnt;
                         }
                     }
                 };

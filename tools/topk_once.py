@@ -23,4 +23,4 @@ for _ in range(reps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
-print(f"N {N} Q {Q}: {ms:.3f} ms per search, {Q / ms * 1e3:.0f} queries/s, {32.0 * Q * N / ms / 1e9:.2f} TFLOP/s fp32, self-hit {(idx[:, 0] == torch.arange(Q, device='cuda')).float().mean().item():.3f}")
+print(f"N {N} Q {Q}: {ms:.3f} ms per search, {Q / ms * 1e3:.0f} queries/s, {32.0 * Q * N / ms / 1e9:.2f} TFLOP/s fp32, {(64.0 * N + 64.0 * Q + 120.0 * Q) / ms / 1e6:.0f} GB/s algorithmic, self-hit {(idx[:, 0] == torch.arange(Q, device='cuda')).float().mean().item():.3f}")
