@@ -16,7 +16,7 @@
 //     shuffle insertion).  No CTA-wide synchronisation in the steady state.
 //   * ties: dot descending, then row index ascending -- per query the rows are visited in ascending order and tau
 //     only lets strictly larger dots through once the list is full, which is exactly that rule.
-//   * large dictionaries (N >= 400k, Q >= 1024) go through the tensor-core screen of topk_screen.cuh first and only
+//   * batched searches (N >= 65 536 rows, Q >= 2048) go through the tensor-core screen of topk_screen.cuh first and only
 //     the survivors are re-ranked with this arithmetic (topk_rerank_kernel): same lists, bit for bit.
 #include <math.h>
 #include <stdlib.h>
@@ -282,25 +282,179 @@ topk_kernel(const __grid_constant__ CUtensorMap dict_map, const TopkParams p) {
 }
 
 // Merge S partial lists per query (one warp per query). Partials hold shard-local int rows.
-__global__ void topk_merge_parts_kernel(const Entry *parts, int S, long long Q, int k, long long index_base,
-                                        float *out_dot, long long *out_idx, float *out_dist) {
-    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (q >= Q) return;
+// The S*k entries of a query are read 32 at a time (coalesced, independent loads) and only those that beat the running
+// k-th best are inserted: the first version walked them one by one with dependent loads and took 440 us for the
+// 296 partial lists of a 10 M-row single-query search -- more than the search itself.
+__global__ void __launch_bounds__(kThreads) topk_merge_parts_kernel(const Entry *parts, int S, long long Q, int k,
+                                                                    long long index_base, float *out_dot,
+                                                                    long long *out_idx, float *out_dist) {
+    // one CTA per query: each warp merges a slice of the S*k entries (two coalesced 32-entry loads in flight), warp 0
+    // merges the eight lists
+    __shared__ Entry lists_s[kWarps][kListLen];
+    const long long q = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float e_dot = -INFINITY;
     int e_idx = kIdxEmpty;
-    for (int s = 0; s < S; ++s) {
-        const Entry *src = parts + ((long long)s * Q + q) * k;
-        for (int j = 0; j < k; ++j) {
-            const Entry cd = src[j];
-            if (cd.idx == kIdxEmpty) break;  // lists are sorted, empties are at the tail
-            warp_insert<int>(e_dot, e_idx, cd.dot, cd.idx, lane);
+    const int total = S * k;
+    const int per_warp = ((total + kWarps - 1) / kWarps + 63) / 64 * 64;
+    const int t_end = (warp + 1) * per_warp < total ? (warp + 1) * per_warp : total;
+    auto fetch = [&](int t) {
+        Entry e;
+        e.dot = -INFINITY;
+        e.idx = kIdxEmpty;
+        if (t < t_end) {
+            const int sp = t / k, j = t - sp * k;
+            e = parts[((long long)sp * Q + q) * k + j];
         }
+        return e;
+    };
+    auto offer = [&](const Entry &e) {
+        const float kd = __shfl_sync(0xffffffffu, e_dot, k - 1);
+        const int ki = __shfl_sync(0xffffffffu, e_idx, k - 1);
+        unsigned m = __ballot_sync(0xffffffffu, e.idx != kIdxEmpty && beats(e.dot, e.idx, kd, ki));
+        while (m) {  // warp-uniform
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            warp_insert<int>(e_dot, e_idx, __shfl_sync(0xffffffffu, e.dot, src), __shfl_sync(0xffffffffu, e.idx, src), lane);
+        }
+    };
+    for (int base = warp * per_warp; base < t_end; base += 64) {
+        const Entry a = fetch(base + lane), b = fetch(base + 32 + lane);
+        offer(a);
+        offer(b);
+    }
+    lists_s[warp][lane].dot = e_dot;
+    lists_s[warp][lane].idx = e_idx;
+    __syncthreads();
+    if (warp != 0) return;
+    for (int w = 1; w < kWarps; ++w) {
+        Entry e = lists_s[w][lane];
+        if (lane >= k) e.idx = kIdxEmpty;
+        offer(e);
     }
     if (lane < k) {
         out_dot[q * k + lane] = e_dot;
         out_idx[q * k + lane] = e_idx == kIdxEmpty ? -1ll : index_base + e_idx;
         if (out_dist) out_dist[q * k + lane] = 1.0f - e_dot;
+    }
+}
+
+// K2q: the interactive case (index_pattern: one query, or a handful) over a large dictionary is a pure HBM stream:
+// 64 B per row against 32 FLOP per (query, row).  No shared-memory staging: every lane owns a row, reads its 64 bytes
+// with four 16-byte loads that bypass L1, and the loads of the next batch are in flight while the current one is
+// reduced (register double buffer), so each SM keeps >= 64 KiB outstanding.  Queries are broadcast from shared
+// memory; the dot is the canonical fma chain; a warp walks a contiguous ascending row range and keeps TQ lists in
+// registers (lane l = entry l), so the strict `dot > tau` filter gives the (dot desc, row asc) order; the 8 warps
+// of a CTA merge through shared memory and each CTA writes one partial list per query for topk_merge_parts_kernel.
+constexpr int kStreamU = 2;   // rows per lane and batch
+
+template <int TQ>
+__global__ void __launch_bounds__(kThreads, TQ <= 2 ? 3 : 2)
+topk_stream_kernel(const float *__restrict__ dict, const TopkParams p, long long rows_per_warp) {
+    __shared__ float4 qs[TQ][4];
+    __shared__ Entry lists_s[kWarps][TQ][kListLen];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < TQ * 4) {
+        const int qi = tid >> 2, c = tid & 3;
+        qs[qi][c] = qi < p.Q ? *(const float4 *)(p.queries + (long long)qi * kD + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const long long gw = (long long)blockIdx.x * kWarps + warp;
+    const long long r_begin = gw * rows_per_warp;
+    long long r_end = r_begin + rows_per_warp;
+    if (r_end > p.N) r_end = p.N;
+
+    float e_dot[TQ], tau[TQ];
+    int e_idx[TQ];
+#pragma unroll
+    for (int qi = 0; qi < TQ; ++qi) {
+        e_dot[qi] = -INFINITY;
+        e_idx[qi] = kIdxEmpty;
+        tau[qi] = -INFINITY;
+    }
+    auto load = [&](long long r0, float4 (&d)[kStreamU][4]) {
+#pragma unroll
+        for (int u = 0; u < kStreamU; ++u) {
+            const long long row = r0 + u * 32 + lane;
+            if (row < r_end) {
+                const float4 *src = (const float4 *)(dict + row * kD);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(d[u][c].x), "=f"(d[u][c].y), "=f"(d[u][c].z), "=f"(d[u][c].w)
+                                 : "l"(src + c));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) d[u][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    };
+    float4 cur[kStreamU][4], nxt[kStreamU][4];
+    if (r_begin < r_end) load(r_begin, cur);
+    for (long long r0 = r_begin; r0 < r_end; r0 += kStreamU * 32) {
+        if (r0 + kStreamU * 32 < r_end) load(r0 + kStreamU * 32, nxt);
+        float acc[TQ][kStreamU];
+        bool hit = false;
+#pragma unroll
+        for (int qi = 0; qi < TQ; ++qi) {
+            const float4 q0 = qs[qi][0], q1 = qs[qi][1], q2 = qs[qi][2], q3 = qs[qi][3];
+#pragma unroll
+            for (int u = 0; u < kStreamU; ++u) {
+                float a = 0.f;
+                a = fmaf(q0.x, cur[u][0].x, a); a = fmaf(q0.y, cur[u][0].y, a); a = fmaf(q0.z, cur[u][0].z, a); a = fmaf(q0.w, cur[u][0].w, a);
+                a = fmaf(q1.x, cur[u][1].x, a); a = fmaf(q1.y, cur[u][1].y, a); a = fmaf(q1.z, cur[u][1].z, a); a = fmaf(q1.w, cur[u][1].w, a);
+                a = fmaf(q2.x, cur[u][2].x, a); a = fmaf(q2.y, cur[u][2].y, a); a = fmaf(q2.z, cur[u][2].z, a); a = fmaf(q2.w, cur[u][2].w, a);
+                a = fmaf(q3.x, cur[u][3].x, a); a = fmaf(q3.y, cur[u][3].y, a); a = fmaf(q3.z, cur[u][3].z, a); a = fmaf(q3.w, cur[u][3].w, a);
+                if (r0 + u * 32 + lane >= r_end) a = -INFINITY;
+                acc[qi][u] = a;
+                hit |= a > tau[qi];
+            }
+        }
+        if (__any_sync(0xffffffffu, hit)) {
+#pragma unroll
+            for (int qi = 0; qi < TQ; ++qi)
+#pragma unroll
+                for (int u = 0; u < kStreamU; ++u) {
+                    unsigned m = __ballot_sync(0xffffffffu, acc[qi][u] > tau[qi]);
+                    while (m) {  // warp-uniform; rows in ascending order
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float cd = __shfl_sync(0xffffffffu, acc[qi][u], src);
+                        if (!(cd > tau[qi])) continue;   // tau may have risen since the ballot
+                        warp_insert<int>(e_dot[qi], e_idx[qi], cd, (int)(r0 + u * 32 + src), lane);
+                        tau[qi] = __shfl_sync(0xffffffffu, e_dot[qi], p.k - 1);  // -inf until k entries
+                    }
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < kStreamU; ++u)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cur[u][c] = nxt[u][c];
+    }
+    // ---- CTA merge: warp qi collects query qi's eight lists
+#pragma unroll
+    for (int qi = 0; qi < TQ; ++qi) {
+        lists_s[warp][qi][lane].dot = e_dot[qi];
+        lists_s[warp][qi][lane].idx = e_idx[qi];
+    }
+    __syncthreads();
+    if (warp < TQ && warp < p.Q) {
+        float m_dot = -INFINITY;
+        int m_idx = kIdxEmpty;
+        for (int w = 0; w < kWarps; ++w) {
+            const Entry e = lists_s[w][warp][lane];
+            for (int j = 0; j < p.k; ++j) {
+                const int ci = __shfl_sync(0xffffffffu, e.idx, j);
+                if (ci == kIdxEmpty) break;  // sorted: empties at the tail
+                warp_insert<int>(m_dot, m_idx, __shfl_sync(0xffffffffu, e.dot, j), ci, lane);
+            }
+        }
+        if (lane < p.k) {
+            Entry o;
+            o.dot = m_dot;
+            o.idx = m_idx;
+            p.parts[((long long)blockIdx.x * p.Q + warp) * p.k + lane] = o;
+        }
     }
 }
 
@@ -522,16 +676,17 @@ static bool screen_enabled() {
     return on == 1;
 }
 
-// The screen pays off once there are enough (query, row) pairs to amortise the operand conversion and the re-rank.
+// The screen pays off once there are enough (query, row) pairs to amortise the operand conversion, the seeding search
+// and the re-rank.  Measured switch-over (gpurun_out/sweep_screen.log, profiles/README.md): at 65 536 rows the screen
+// wins from ~2k queries on (0.30 vs 0.41 ms at Q = 4096, 0.68 vs 1.12 ms at Q = 16 384); at 30 000 rows or 1024
+// queries the CUDA-core kernel is as fast or faster.  EBSD_TOPK_SCREEN_MIN_ROWS moves the row threshold for A/B timing.
 static bool screen_applies(long long N, long long Q, int k) {
-    // measured (profiles/README.md): the screen is bound by draining the accumulators from TMEM (one fp32 per pair,
-    // ~2 us per 128 x 256 tile) and wins over the CUDA-core kernel only for large dictionaries
     static long long min_rows = -1;
     if (min_rows < 0) {
-        const char *e = getenv("EBSD_TOPK_SCREEN_MIN_ROWS");   // A/B timing of the switch-over point
-        min_rows = (e && atoll(e) > 0) ? atoll(e) : 400000;
+        const char *e = getenv("EBSD_TOPK_SCREEN_MIN_ROWS");
+        min_rows = (e && atoll(e) > 0) ? atoll(e) : 65536;
     }
-    return screen_enabled() && k < kScrCap / 2 && N >= min_rows && Q >= 1024 && N < 0x7fffff00ll;
+    return screen_enabled() && k < kScrCap / 2 && N >= min_rows && Q >= 2048 && N < 0x7fffff00ll;
 }
 
 static ScreenPlan make_screen_plan(long long N, long long Q, int sms) {
@@ -601,9 +756,70 @@ static int launch_topk(const CUtensorMap &map, const TopkParams &p, int sms, cud
     return EBSD_OK;
 }
 
+// K2q applies to a handful of queries over a dictionary long enough to give every warp a few batches.
+constexpr long long kStreamMaxQ = 8;
+static bool stream_applies(long long N, long long Q) {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("EBSD_TOPK_STREAM");   // 0: keep the tiled kernel (A/B timing)
+        on = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return on == 1 && Q <= kStreamMaxQ && N >= 32768;
+}
+static int stream_tq(long long Q) { return Q <= 1 ? 1 : (Q <= 2 ? 2 : (Q <= 4 ? 4 : 8)); }
+// CTAs of the stream kernel (= partial lists per query): every resident slot, but at least 4 batches per warp
+static int stream_grid(long long N, long long Q, int sms) {
+    const int slots = sms * (stream_tq(Q) <= 2 ? 3 : 2);
+    const long long by_rows = N / (kWarps * kStreamU * 32 * 4);
+    return (int)(by_rows < 1 ? 1 : (by_rows < slots ? by_rows : slots));
+}
+static size_t exact_workspace_bytes(long long N, long long Q, int k, int sms) {
+    if (stream_applies(N, Q)) return (size_t)stream_grid(N, Q, sms) * (size_t)Q * (size_t)k * sizeof(Entry);
+    const TopkPlan pl = make_plan(N, Q, sms);
+    return pl.n_splits > 1 ? (size_t)pl.n_splits * (size_t)Q * (size_t)k * sizeof(Entry) : 0;
+}
+
+template <int TQ>
+static int launch_stream(const float *dict, const TopkParams &p, int grid, long long rows_per_warp, cudaStream_t st) {
+    topk_stream_kernel<TQ><<<grid, kThreads, 0, st>>>(dict, p, rows_per_warp);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}
+
+static int run_stream(const float *dict, long long N, long long index_base, const float *queries, long long Q, int k,
+                      float *out_dot, long long *out_idx, float *out_dist, void *workspace, int sms, cudaStream_t st) {
+    const int grid = stream_grid(N, Q, sms);
+    const long long warps = (long long)grid * kWarps;
+    const long long batch = kStreamU * 32;
+    const long long rows_per_warp = ((N + warps - 1) / warps + batch - 1) / batch * batch;
+    TopkParams p;
+    p.queries = queries;
+    p.Q = Q;
+    p.N = N;
+    p.index_base = index_base;
+    p.k = k;
+    p.n_qtiles = 1;
+    p.n_splits = grid;
+    p.tiles_per_split = 0;
+    p.parts = (Entry *)workspace;
+    p.out_dot = out_dot;
+    p.out_idx = out_idx;
+    p.out_dist = out_dist;
+    const int tq = stream_tq(Q);
+    int rc = tq == 1 ? launch_stream<1>(dict, p, grid, rows_per_warp, st)
+                     : (tq == 2 ? launch_stream<2>(dict, p, grid, rows_per_warp, st)
+                                : (tq == 4 ? launch_stream<4>(dict, p, grid, rows_per_warp, st)
+                                           : launch_stream<8>(dict, p, grid, rows_per_warp, st)));
+    if (rc) return rc;
+    topk_merge_parts_kernel<<<(unsigned)Q, kThreads, 0, st>>>(p.parts, grid, Q, k, index_base, out_dot, out_idx, out_dist);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}
+
 // The exact CUDA-core search of `N` rows (workspace: n_splits * Q * k entries when the plan splits the dictionary).
 static int run_exact(const float *dict, long long N, long long index_base, const float *queries, long long Q, int k,
                      float *out_dot, long long *out_idx, float *out_dist, void *workspace, int sms, cudaStream_t st) {
+    if (stream_applies(N, Q)) return run_stream(dict, N, index_base, queries, Q, k, out_dot, out_idx, out_dist, workspace, sms, st);
     const TopkPlan pl = make_plan(N, Q, sms);
     tensormap_encode_fn encode = get_tensormap_encode();
     if (!encode) {
@@ -639,9 +855,8 @@ static int run_exact(const float *dict, long long N, long long index_base, const
                         : (pl.tq == 4 ? launch_topk<4>(map, p, sms, st) : launch_topk<1>(map, p, sms, st));
     if (rc) return rc;
     if (pl.n_splits > 1) {
-        const int wpb = 8;
-        topk_merge_parts_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, st>>>(p.parts, pl.n_splits, Q, k, index_base,
-                                                                                    out_dot, out_idx, out_dist);
+        topk_merge_parts_kernel<<<(unsigned)Q, kThreads, 0, st>>>(p.parts, pl.n_splits, Q, k, index_base, out_dot, out_idx,
+                                                                 out_dist);
         EBSD_LAUNCH_CHECK();
     }
     return EBSD_OK;
@@ -736,8 +951,7 @@ int ebsd_normalize_rows(float *x, int64_t n, int d, void *stream) {
 size_t ebsd_topk_workspace_bytes(int64_t N, int64_t Q, int k) {
     if (N <= 0 || Q <= 0 || k <= 0) return 0;
     if (screen_applies(N, Q, k)) return make_screen_plan(N, Q < kScreenQueryChunk ? Q : kScreenQueryChunk, sm_count()).bytes;
-    const TopkPlan pl = make_plan(N, Q, sm_count());
-    return pl.n_splits > 1 ? (size_t)pl.n_splits * (size_t)Q * (size_t)k * sizeof(Entry) : 0;
+    return exact_workspace_bytes(N, Q, k, sm_count());
 }
 
 int ebsd_topk(const float *dict, int64_t N, int64_t index_base, const float *queries, int64_t Q, int k,
@@ -778,8 +992,7 @@ int ebsd_topk(const float *dict, int64_t N, int64_t index_base, const float *que
         }
         return EBSD_OK;
     }
-    const TopkPlan pl = make_plan(N, Q, sms);
-    const size_t need = pl.n_splits > 1 ? (size_t)pl.n_splits * (size_t)Q * (size_t)k * sizeof(Entry) : 0;
+    const size_t need = exact_workspace_bytes(N, Q, k, sms);
     if (need > 0 && (workspace == nullptr || workspace_bytes < need)) {
         set_error("ebsd_topk: workspace too small (%zu < %zu)", workspace_bytes, need);
         return EBSD_ERR_WORKSPACE;

@@ -48,6 +48,9 @@ def test_normalize_rows_bit_exact():
     (625, 1, 10, 0.0), (625, 1, 20, 0.0), (1000, 5, 20, 0.01), (5000, 200, 10, 0.01), (127, 3, 10, 0.0),
     (128, 16, 10, 0.0), (129, 17, 32, 0.0), (7, 4, 10, 0.0), (100_000, 300, 10, 0.001), (33_333, 1000, 1, 0.01),
     (20_000, 129, 10, 0.3),
+    # K2q, the streaming kernel for a handful of queries over >= 32 768 rows (one lane per row, TQ = 1, 2, 4, 8)
+    (32_768, 1, 10, 0.0), (200_013, 1, 10, 0.2), (150_001, 2, 32, 0.3), (99_999, 3, 10, 0.3), (400_000, 5, 1, 0.1),
+    (65_537, 8, 20, 0.5),
 ])
 def test_topk_bit_exact_vs_oracle(n, q, k, dup):
     d, qs = _data(n, q, seed=n + q + k, dup=dup)
@@ -140,14 +143,14 @@ def test_full_size_properties_1m_rows():
     np.testing.assert_array_equal(dot[:48].cpu().numpy(), odot)
 
 
-def test_tensor_core_screen_equals_exact_kernel_incl_overflow_fallback():
-    """for large dictionaries ebsd_topk screens with tensor cores and re-ranks the survivors with the
+@pytest.mark.parametrize("n,q", [(420_000, 2500), (301_000, 2100)])
+def test_tensor_core_screen_equals_exact_kernel_incl_overflow_fallback(n, q):
+    """for batched searches (N >= 65 536, Q >= 2048) ebsd_topk screens with tensor cores and re-ranks the survivors with the
     canonical arithmetic.  Its lists must equal the CUDA-core kernel's bit for bit -- also for queries whose k-th best
     dot is shared by hundreds of duplicate rows (survivor buffers overflow -> exact scan of the range) -- and the
     sampled oracle check pins both to the restatement."""
     import os
     g = torch.Generator(device="cuda").manual_seed(77)
-    n, q = 420_000, 1500
     d = torch.randn((n, 16), generator=g, device="cuda")
     d[100_000:100_700] = d[5]                     # 700 exact copies of row 5
     d[300_000:300_040] = d[6] * 3.0               # 40 rescaled copies of row 6 (identical after normalisation)
@@ -158,10 +161,10 @@ def test_tensor_core_screen_equals_exact_kernel_incl_overflow_fallback():
     qs[0] = d[5]
     qs[1] = d[6]
     qh = db._prepare_queries(qs)
-    dot_s, idx_s, _ = db.search_device(qh, 10)                       # screen path (N >= 400k, Q >= 1024)
+    dot_s, idx_s, _ = db.search_device(qh, 10)                       # screen path (N >= 65 536, Q >= 2048)
     os.environ["EBSD_TOPK_SCREEN_OFF_FOR_TEST"] = "1"
     try:
-        dot_e, idx_e, _ = db.search_device(qh[:1000].contiguous(), 10)   # Q < 1024 -> CUDA-core kernel
+        dot_e, idx_e, _ = db.search_device(qh[:1000].contiguous(), 10)   # Q < 2048 -> CUDA-core kernel
     finally:
         del os.environ["EBSD_TOPK_SCREEN_OFF_FOR_TEST"]
     assert torch.equal(idx_s[:1000], idx_e) and torch.equal(dot_s[:1000], dot_e)
