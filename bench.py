@@ -99,6 +99,37 @@ def time_blocks(torch, engine, lib, n_img: int = 1184):
     return out
 
 
+def time_topk_stream(torch, peaks, device, n_rows: int = 10_000_000, reps: int = 20):
+    """index_pattern's search (ONE query) over a 10 M-row dictionary (640 MB of fp32 rows, 5x the L2): the HBM-bound
+    regime of ebsd_topk (kernel topk_stream_kernel + partial-list merge), algorithmic bytes 64 N + 64 Q + 12 k Q."""
+    import ebsd_vae_b200 as E
+
+    g = torch.Generator(device=device).manual_seed(7)
+    big = E.LatentVectorDatabase()
+    big.add_vectors(torch.randn((n_rows, 16), generator=g, device=device),
+                    torch.zeros((n_rows, 3), dtype=torch.float64, device=device))
+    q1 = big._prepare_queries(torch.randn((1, 16), generator=g, device=device))
+    for _ in range(3):
+        big.search_device(q1, TOP_N)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(reps):
+        big.search_device(q1, TOP_N)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / reps
+    nbytes = 64 * n_rows + 64 + 12 * TOP_N
+    out = {"dictionary_rows": n_rows, "queries": 1, "ms": ms, "hbm_gbs": nbytes / (ms * 1e-3) / 1e9,
+           "hbm_frac_of_measured": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+           "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})",
+           "note": "whole ebsd_topk call (stream kernel + merge of the per-CTA lists), CUDA events over %d back-to-back "
+                   "searches" % reps}
+    del big
+    torch.cuda.empty_cache()
+    return out
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -420,6 +451,9 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
         "algorithmic_flop_per_pattern": F_ENC,
         "precision_note": "fp32-accurate convolution = three fp16 tensor-core products per algorithmic MAC, so the "
                           "algorithmic ceiling is 1/3 of the tensor peak (frac <= 0.333)",
+        "tensor_pipe": {"mma_tflops": 3.0 * enc_tflops, "frac_of_peak": 3.0 * enc_tflops / peak_tf,
+                        "note": "fp16 tensor-core work actually issued (three MMAs per algorithmic MAC) against the same "
+                                "measured cuBLAS bf16 figure = tensor-pipe utilisation of the encoder chain"},
         "blocks": time_blocks(torch, engine, lib) if rank == 0 else None,
     }
     stages = {
@@ -428,7 +462,11 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
         "topk_fp32_tflops": topk_flop / (topk_ms * 1e-3) / 1e12,
         "topk_queries_per_s": N_QUERY_PER_GPU / (topk_ms * 1e-3),
         "consensus_queries_per_s": N_QUERY_PER_GPU / (cons_ms * 1e-3),
+        "topk_bound": "the batched search (thousands of queries per pass) is bound by tensor-core / TMEM-drain work, not "
+                      "HBM; the HBM-bound regime is the single-query search in topk_stream",
     }
+    if rank == 0 and world == 1 and not CUSTOM_WORKLOAD:
+        stages["topk_stream"] = time_topk_stream(torch, peaks, device)
 
     # search quality next to the numbers: the reference's Chroma/HNSW index is approximate, this search is exact.
     # chromadb / hnswlib are not installable in this image (no network), so their recall cannot be measured here;

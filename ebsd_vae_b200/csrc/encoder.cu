@@ -462,8 +462,9 @@ int fused_weight_box_rows(int layer) {
     return (EBSD_PAIR && kPlan[layer].cin >= 64) ? cout / 2 : 2 * cout;  // FusedCfg::PAIR, B_BOX_ROWS
 }
 
-// fp32 [nimg,Wo,Wo,COUT] output as a 4-D tensor (c, x, y, n); box = (32 channels, bx, by, bn), 128B-swizzled in smem
-int make_out_map(CUtensorMap *map, const float *base, int cout, int wo, int nimg, int bx, int by, int bn) {
+// fp32 [nimg,Wo,Wo,COUT] output as a 4-D tensor (c, x, y, n); box = (32 channels, bx, by, bn), 128B-swizzled in smem,
+// or (bc = 16 channels, ...) with 64-byte rows and the 64B swizzle (the front-end block's half-channel boxes)
+int make_out_map(CUtensorMap *map, const float *base, int cout, int wo, int nimg, int bx, int by, int bn, int bc = 32) {
     tensormap_encode_fn encode = get_tensormap_encode();
     if (!encode) {
         set_error("encoder: cuTensorMapEncodeTiled entry point not available");
@@ -471,10 +472,10 @@ int make_out_map(CUtensorMap *map, const float *base, int cout, int wo, int nimg
     }
     const cuuint64_t gdim[4] = {(cuuint64_t)cout, (cuuint64_t)wo, (cuuint64_t)wo, (cuuint64_t)nimg};
     const cuuint64_t gstride[3] = {(cuuint64_t)cout * 4, (cuuint64_t)wo * cout * 4, (cuuint64_t)wo * wo * cout * 4};
-    const cuuint32_t box[4] = {32u, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bn};
+    const cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bn};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, gdim, gstride, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, bc == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
         set_error("encoder: cuTensorMapEncodeTiled(raw output) failed with %d", (int)cr);
@@ -524,7 +525,7 @@ int launch_fused(const ebsd_encoder *enc, int layer, const void *src, const doub
     } else {
         memset(&map_src, 0, sizeof(map_src));
     }
-    if (C::NI == 1) rc = make_out_map(&map_out, raw, COUT, POOL ? W / 2 : W, nimg, POOL ? 4 : 8, POOL ? 2 : 4, 1);
+    if (C::NI == 1) rc = make_out_map(&map_out, raw, COUT, POOL ? W / 2 : W, nimg, POOL ? 4 : 8, POOL ? 2 : 4, 1, C::ACCUM ? 16 : 32);
     else rc = make_out_map(&map_out, raw, COUT, POOL ? W / 2 : W, nimg, POOL ? 4 : 8, POOL ? 1 : 2, 2);
     if (rc) return rc;
     FusedParams p;

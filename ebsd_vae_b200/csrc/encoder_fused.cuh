@@ -89,6 +89,11 @@ struct FusedCfg {
     static constexpr int B_BOX_ROWS = PAIR ? COUT / 2 : 2 * COUT;  // rows of one weight TMA box
     static constexpr int A_STAGES = (W >= 128 && EBSD_FRONT_NT == 2) ? 4 : 2;
     static constexpr int PATCH_W = 8 * NT + 4, PATCH_H = 20;   // FIRST: input pixels a window needs (conv0 + conv1 halos)
+    // row stride of the patch in shared memory.  A producer warp reads 32 consecutive window positions, which wrap to
+    // the next window row after PITCH of them; with a stride of PITCH + 32 words the lanes after the wrap stay on the
+    // banks they would have had without it (stride 36: the last two lanes collided with the first two on nearly every
+    // load, 1.8 wavefronts per LDS, ncu)
+    static constexpr int PATCH_S = PITCH + 32;
     // output staging for the TMA stores: per epilogue warp one [32 or 8 rows][128 B] box, 128B-swizzled
     static constexpr int WSTG = POOL ? 1024 : 4096;
     // COUT = 32 with several tiles per item (the front end): the epilogue walks 16-channel halves outside the tile
@@ -301,7 +306,8 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     uint64_t *tempty_bar = tfull_bar + 2;            // [2]
     uint32_t *tmem_slot = (uint32_t *)(tempty_bar + 2);
     const uint32_t tab_u32 = smem_u32(extra + 512);     // float2 [NI][CIN] (scale, shift) of the source planes: <= 2 KB
-    const uint32_t patch_u32 = smem_u32(extra + 3840);  // FIRST: float [20][36] input pixels (2880 B) -> ends at 6720
+    const uint32_t patch_u32 = smem_u32(extra + 2560);  // FIRST: float [PATCH_H][PATCH_S] input pixels (5280 B) -> ends at 7840
+    static_assert(!C::FIRST || (2560 + C::PATCH_H * C::PATCH_S * 4 <= 8192 && C::PATCH_S >= C::PATCH_W), "conv0 patch does not fit");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -599,17 +605,18 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                             const float keep = b_par ? r[4 + i] : r[i];
                             o[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, PV));
                         }
-                        const uint32_t stg = stg_u32 + (uint32_t)(t * C::WSTG);
-                        const int ch = hf * 4 + a_par * 2 + b_par;  // 16-byte chunk of this lane's 4 channels
-                        sts128(stg + (uint32_t)(prow * 128) + (uint32_t)((ch ^ (prow & 7)) << 4),
+                        // one box per (tile, 16-channel half): 8 pooled pixels x 64 B, 64B-swizzled.  With 128-byte rows
+                        // the eight lanes of a store phase hit only four 16-byte bank groups (two wavefronts per
+                        // phase, ncu); with 64-byte rows they cover all eight.
+                        const uint32_t stg = stg_u32 + (uint32_t)(t * C::WSTG + hf * 512);
+                        const int ch = a_par * 2 + b_par;  // 16-byte chunk of this lane's 4 channels inside the half
+                        sts128(stg + (uint32_t)(prow * 64) + (uint32_t)((ch ^ ((prow >> 1) & 3)) << 4),
                                make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])));
-                        if (hf == 1) {
-                            fence_proxy_async();
-                            __syncwarp();
-                            if (lane == 0 && n < p.nimg && !(p.dbg & 16)) {
-                                tma_store_4d(&map_out, stg, 0, (x0 + 8 * t) >> 1, (y0 + 4 * quarter) >> 1, n);
-                                bulk_commit();
-                            }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0 && n < p.nimg && !(p.dbg & 16)) {
+                            tma_store_4d(&map_out, stg, hf * 16, (x0 + 8 * t) >> 1, (y0 + 4 * quarter) >> 1, n);
+                            bulk_commit();
                         }
                     }
                     if (!(p.dbg & 8)) {
@@ -795,7 +802,9 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     if (ptid + C::PRODUCERS * i < C::PATCH_H * C::PATCH_W) {
                         // ToTensor: uint8 -> float32, true division by 255 (latice/data_module.py:31)
                         const float v = SRC == SRC_U8 ? (float)pv[i] / 255.0f : __uint_as_float(pv[i]);
-                        sts32(patch_u32 + (ptid + C::PRODUCERS * i) * 4, __float_as_uint(v));
+                        const int idx = ptid + C::PRODUCERS * i;
+                        const int py = idx / C::PATCH_W, px = idx - py * C::PATCH_W;
+                        sts32(patch_u32 + (py * C::PATCH_S + px) * 4, __float_as_uint(v));
                     }
                 named_bar_sync(1, C::PRODUCERS);
                 if (item + 1 < item_end) load_patch(item + 1);
@@ -818,7 +827,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                             for (int dx = 0; dx < 3; ++dx) {
-                                const float v = lds32(patch_u32 + ((wy + dy) * C::PATCH_W + wx + dx) * 4);
+                                const float v = lds32(patch_u32 + ((wy + dy) * C::PATCH_S + wx + dx) * 4);
                                 const float2 vv = make_float2(v, v);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) acc[j] = __ffma2_rn(vv, wreg[dy * 3 + dx][j], acc[j]);
