@@ -125,9 +125,9 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
     uint64_t *d_empty = d_full + kScrStages;            // [stages]
     uint64_t *q_full = d_empty + kScrStages;            // [1]
     uint64_t *q_empty = q_full + 1;                     // [1]
-    uint64_t *tfull = q_empty + 1;                      // [2]
-    uint64_t *tempty = tfull + 2;                       // [2]
-    uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
+    uint64_t *tfull = q_empty + 1;                      // [4]: accumulator (tile parity, column half) -- see the MMA loop
+    uint64_t *tempty = tfull + 4;                       // [4]
+    uint32_t *tmem_slot = (uint32_t *)(tempty + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -137,9 +137,9 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
         }
         mbar_init(q_full, 1);
         mbar_init(q_empty, 1);
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 4; ++b) {
             mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], 4 * kScrGroups);
+            mbar_init(&tempty[b], 2 * kScrGroups);   // the 8 warps (4 lane quarters x 2 column groups) of one half
         }
         mbar_fence_init();
         tma_prefetch_desc(&map_d);
@@ -177,7 +177,11 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
     } else if (warp == 1) {
         // ===================== MMA: s~ = q_hi.d_hi + q_hi.d_lo + q_lo.d_hi, one accumulator per dictionary tile
         if (elect_one_sync()) {
-            constexpr uint32_t idesc = umma_idesc_f16(kScrN);
+            // A 256-row dictionary tile is computed as two 128-column halves with their own TMEM accumulator and
+            // barriers: the epilogue warps of half 0 and of half 1 form two independent double-buffered pipelines, so
+            // the MMA -> drain -> release round trip of one half overlaps the other's (with one 256-column
+            // accumulator per tile the hand-off was a latency chain: ~1400 cycles per tile against a 450-cycle drain).
+            constexpr uint32_t idesc = umma_idesc_f16(kScrN / 2);
             unsigned it = 0, qit = 0, tj = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++qit) {
                 const int split = item / p.n_qtiles;
@@ -188,17 +192,21 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
                 tc_fence_after();
                 const uint32_t qa = smem_u32(smem_q);
                 for (long long t = tile0; t < tile1; ++t, ++it, ++tj) {
-                    const int s = it % kScrStages, buf = tj & 1;
-                    mbar_wait_bounded(&tempty[buf], ((tj >> 1) & 1u) ^ 1u);
+                    const int s = it % kScrStages;
                     mbar_wait_bounded(&d_full[s], (it / kScrStages) & 1u);
-                    tc_fence_after();
-                    const uint32_t db = smem_u32(smem_d + s * kScrTileB);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kScrN);
-                    umma_f16(d_tmem, umma_smem_desc<kScrRowB>(qa), umma_smem_desc<kScrRowB>(db), idesc, 0u);            // hi.hi
-                    umma_f16(d_tmem, umma_smem_desc<kScrRowB>(qa), umma_smem_desc<kScrRowB>(db + 32), idesc, 1u);       // hi.lo
-                    umma_f16(d_tmem, umma_smem_desc<kScrRowB>(qa + 32), umma_smem_desc<kScrRowB>(db), idesc, 1u);       // lo.hi
-                    umma_commit(&d_empty[s]);
-                    umma_commit(&tfull[buf]);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int buf = (int)(tj & 1) * 2 + half;
+                        mbar_wait_bounded(&tempty[buf], ((tj >> 1) & 1u) ^ 1u);
+                        tc_fence_after();
+                        const uint32_t db = smem_u32(smem_d + s * kScrTileB) + (uint32_t)(half * (kScrN / 2) * kScrRowB);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * (kScrN / 2));
+                        umma_f16(d_tmem, umma_smem_desc<kScrRowB>(qa), umma_smem_desc<kScrRowB>(db), idesc, 0u);            // hi.hi
+                        umma_f16(d_tmem, umma_smem_desc<kScrRowB>(qa), umma_smem_desc<kScrRowB>(db + 32), idesc, 1u);       // hi.lo
+                        umma_f16(d_tmem, umma_smem_desc<kScrRowB>(qa + 32), umma_smem_desc<kScrRowB>(db), idesc, 1u);       // lo.hi
+                        if (half == 1) umma_commit(&d_empty[s]);
+                        umma_commit(&tfull[buf]);
+                    }
                 }
                 umma_commit(q_empty);  // the query tile may be replaced once this item's MMAs have read it
             }
@@ -221,10 +229,10 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
             // k prefix rows have exact dots >= tau0, so S_k >= tau0; a row with s~ < tau0 - EPS has s < tau0
             float thr = live ? p.tau0[((long long)qt * kScrM + m) * p.k + (p.k - 1)] - kScrEps : INFINITY;
             for (long long t = tile0; t < tile1; ++t, ++tj) {
-                const int buf = tj & 1;
+                const int buf = (int)(tj & 1) * 2 + (half >> 1);   // accumulator of (tile parity, column half of the tile)
                 mbar_wait_bounded(&tfull[buf], (tj >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kScrN + half * kScrGroupCols);
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((tj & 1) * kScrN + half * kScrGroupCols);
                 const long long row_base = t * kScrN + half * kScrGroupCols;
                 // survivors of one 32-column chunk (rare).  The code is kept SMALL on purpose: the first version inlined
                 // the buffer compaction into each of the 32 unrolled steps (17k SASS instructions, far beyond the
