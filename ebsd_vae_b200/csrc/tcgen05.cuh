@@ -75,6 +75,34 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
     }
 }
 
+// The same wait by 32-bit shared-window address (for hot loops: no generic-pointer conversion per call).
+__device__ __forceinline__ void mbar_wait_bounded_u32(uint32_t bar_u32, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_u32), "r"(parity)
+        : "memory");
+    if (ok) return;
+    const long long t0 = clock64();
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar_u32), "r"(parity), "r"(EBSD_WAIT_HINT_NS)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000ll) {
+            printf("ebsd: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
 // UMMA shared-memory descriptor, K-major operand whose rows are SWB bytes wide (SWB = 64 or 128 = swizzle span).
 template <int SWB>
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {

@@ -215,6 +215,12 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
         // ===================== epilogue: threshold filter, one thread = one query x one column half
         const int quarter = warp & 3, half = (warp - 4) >> 2;   // `half` = column group of this warp
         const int m = quarter * 32 + lane;
+        // shared-window addresses of this warp's two accumulator barriers, computed once (the generic pointers were
+        // re-derived from the aligned dynamic-smem base on every tile: ~20 of ~160 instructions per warp and tile)
+        // (the opaque mov keeps ptxas from rematerialising the address computation inside the loop)
+        uint32_t tfull_u32, tempty_u32;
+        asm volatile("mov.u32 %0, %1;" : "=r"(tfull_u32) : "r"(smem_u32(tfull) + (uint32_t)((half >> 1) * 8)));
+        asm volatile("mov.u32 %0, %1;" : "=r"(tempty_u32) : "r"(smem_u32(tempty) + (uint32_t)((half >> 1) * 8)));
         unsigned tj = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int split = item / p.n_qtiles, qt = item - split * p.n_qtiles;
@@ -229,8 +235,8 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
             // k prefix rows have exact dots >= tau0, so S_k >= tau0; a row with s~ < tau0 - EPS has s < tau0
             float thr = live ? p.tau0[((long long)qt * kScrM + m) * p.k + (p.k - 1)] - kScrEps : INFINITY;
             for (long long t = tile0; t < tile1; ++t, ++tj) {
-                const int buf = (int)(tj & 1) * 2 + (half >> 1);   // accumulator of (tile parity, column half of the tile)
-                mbar_wait_bounded(&tfull[buf], (tj >> 1) & 1u);
+                // accumulator (tile parity, column half of the tile) = barrier index (tj & 1) * 2 + (half >> 1)
+                mbar_wait_bounded_u32(tfull_u32 + (uint32_t)((tj & 1) * 16), (tj >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((tj & 1) * kScrN + half * kScrGroupCols);
                 const long long row_base = t * kScrN + half * kScrGroupCols;
@@ -275,11 +281,12 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
                     float v[32];
                     tmem_ld32(t_row + c0, v);
                     tmem_ld_wait();
-                    if (live && chunk_max(v) >= thr) scan(v, c0);
+                    if (chunk_max(v) >= thr) scan(v, c0);   // queries past Q have thr = +inf
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[buf]);
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_u32 + (uint32_t)((tj & 1) * 16)) : "memory");
             }
             p.cand_n[slot] = cnt;
         }
