@@ -7,18 +7,22 @@
 //
 //   operands   rows and queries as fp16 pairs [hi(16) | lo(16)] (64-byte K-major rows, SWIZZLE_64B): x = hi + lo up
 //              to 2^-22 |x|;  s~ = q_hi.d_hi + q_hi.d_lo + q_lo.d_hi  = three tcgen05.mma (M = 128 queries,
-//              N = 256 rows, K = 16 each) into one fp32 TMEM accumulator.
+//              N = 2 x 128 rows, K = 16 each) into fp32 TMEM accumulators.
 //   error      |s~ - s| <= EPS = 1e-5 for unit vectors: split remainders (<= 4 * 2^-24), fp16 underflow of the lo parts
 //              (<= 16 * 2^-25), 48 fp32 accumulations in the tensor core (<= 48 * 2^-23 even if it truncates) and the
 //              rounding of the canonical chain itself (<= 16 * 2^-24); tests measure the actual maximum (~3e-7).
 //   filter     a query keeps every row with s~ >= thr.  thr starts at tau0 - EPS, tau0 = the query's exact k-th best dot
 //              over a prefix of the dictionary (found by the CUDA-core kernel first), and is raised whenever a
-//              survivor buffer fills up: thr = (k-th largest s~ among rows already kept) - 2 EPS.
+//              survivor buffer runs out of room: thr = (k-th largest s~ among rows already kept) - 2 EPS.
 //              Those k rows have s >= kth - EPS, so the final k-th best exact dot S_k >= kth - EPS, and a dropped row
 //              has s <= s~ + EPS < kth - EPS <= S_k: it cannot be in the top-k, ties included.
-//   layout     TMEM lane = query, column = dictionary row: an epilogue thread owns one query (its threshold lives in
-//              a register) and scans 128 columns per tile; survivors go to a per-(work item, column half, query)
-//              buffer of CAP entries in global memory; a full buffer is compacted in place (k-th largest -> new thr).
+//   layout     TMEM lane = query, column = dictionary row.  A 256-row tile is computed as two 128-column halves with
+//              their own accumulator and barriers (four accumulators = 512 TMEM columns, double-buffered per half);
+//              16 epilogue warps = 4 lane quarters x 4 column groups of 64: an epilogue thread owns one query (its
+//              threshold lives in a register) and scans 64 columns per tile, 32 per tcgen05.ld, with a 3-input max
+//              tree and one compare per chunk; survivors go to a per-(work item, column group, query) buffer of CAP
+//              entries in global memory, compacted out of line when fewer than 32 entries are free (k-th largest
+//              -> new thr).
 //   re-rank    topk_rerank_kernel: one warp per query gathers the surviving rows of all its buffers, recomputes the
 //              canonical fp32 dot and inserts into the (dot desc, row asc) sorted list of the exact kernel.
 #pragma once
@@ -212,7 +216,7 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue: threshold filter, one thread = one query x one column half
+        // ===================== epilogue: threshold filter, one thread = one query x one column group of 64
         const int quarter = warp & 3, half = (warp - 4) >> 2;   // `half` = column group of this warp
         const int m = quarter * 32 + lane;
         // shared-window addresses of this warp's two accumulator barriers, computed once (the generic pointers were
