@@ -174,3 +174,20 @@ def test_tensor_core_screen_equals_exact_kernel_incl_overflow_fallback(n, q):
     odot, oidx = T.topk(dn, qh[:24].cpu().numpy(), 10, nthreads=8)
     np.testing.assert_array_equal(idx_s[:24].cpu().numpy(), oidx)
     np.testing.assert_array_equal(dot_s[:24].cpu().numpy(), odot)
+
+
+@pytest.mark.parametrize("k", [1, 32])
+def test_tensor_core_screen_other_k(k):
+    """The screen path at the ends of the supported k range (EBSD_MAX_TOPK = 32 rides on CAP - 32 = 64 buffer entries),
+    with 30 % duplicated rows so that ties at the k-th place are common: equal to the CUDA-core kernel and the oracle."""
+    d, qs = _data(70_001, 2100, seed=5 + k, dup=0.3)
+    db = _db(d, index_base=7)
+    qh = db._prepare_queries(qs)
+    dot_s, idx_s, _ = db.search_device(qh, k)                           # screen (N >= 65 536, Q >= 2048)
+    dot_e, idx_e, _ = db.search_device(qh[:900].contiguous(), k)        # CUDA-core kernel
+    torch.cuda.synchronize()
+    assert torch.equal(idx_s[:900], idx_e) and torch.equal(dot_s[:900], dot_e)
+    dn = db._latents[:70_001].cpu().numpy()
+    odot, oidx = T.topk(dn, qh[:32].cpu().numpy(), k, index_base=7, nthreads=8)
+    np.testing.assert_array_equal(idx_s[:32].cpu().numpy(), oidx)
+    np.testing.assert_array_equal(dot_s[:32].cpu().numpy(), odot)
