@@ -20,7 +20,8 @@
 //     (y + dy) * 20 + image * 10 + dx = 10 j + ...: stride 10.
 // Zero padding is simply zeros the producers write at halo positions outside the image.
 //
-// Warp roles (512 threads): warp 0 weight TMA, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
+// Warp roles (512 threads): warp 0 weight TMA, warp 1 MMA issuer, warp 2 TMEM allocator, warp 3 conv0 patch staging
+// (front-end block only), warps 4-7 epilogue
 // (TMEM lane quarter = warp & 3), warps 8-15 producers (two per scheduler: global-load and ALU latency overlap).
 #pragma once
 #include "encoder_mma.cuh"
@@ -101,7 +102,10 @@ struct FusedCfg {
     static constexpr bool ACCUM = COUT == 32 && NT > 1;
     static constexpr int NSB = ACCUM ? NT : (!POOL ? (RESIDENT_B ? EBSD_NSB_RESIDENT : EBSD_NSB_STREAMED) : 1);  // staging boxes per warp
     static constexpr int STAGING = 4 * NSB * WSTG;
-    static constexpr int EXTRA = 8192 + STAGING;             // barriers, tables, conv0 patch | staging
+    // barriers + tables (+ FIRST: two conv0 patches of PATCH_BYTES, written by a helper warp one item ahead) | staging
+    static constexpr int PATCH_BYTES = (PATCH_H * PATCH_S * 4 + 127) / 128 * 128;
+    static constexpr int XBASE = FIRST ? (2560 + 2 * PATCH_BYTES + 1023) / 1024 * 1024 : 8192;
+    static constexpr int EXTRA = XBASE + STAGING;
     static constexpr int B_FIT = (226 * 1024 - 1024 - EXTRA - A_STAGES * A_STAGE) / B_CTA;
     static constexpr int B_STAGES = RESIDENT_B ? 9 * NCHUNK : (B_FIT > 8 ? 8 : B_FIT);
     static constexpr int B_BYTES = B_STAGES * B_CTA;
@@ -306,8 +310,11 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     uint64_t *tempty_bar = tfull_bar + 2;            // [2]
     uint32_t *tmem_slot = (uint32_t *)(tempty_bar + 2);
     const uint32_t tab_u32 = smem_u32(extra + 512);     // float2 [NI][CIN] (scale, shift) of the source planes: <= 2 KB
-    const uint32_t patch_u32 = smem_u32(extra + 2560);  // FIRST: float [PATCH_H][PATCH_S] input pixels (5280 B) -> ends at 7840
-    static_assert(!C::FIRST || (2560 + C::PATCH_H * C::PATCH_S * 4 <= 8192 && C::PATCH_S >= C::PATCH_W), "conv0 patch does not fit");
+    uint64_t *patch_full = (uint64_t *)(extra + 256);   // [2] FIRST: patch buffer written (helper warp -> producers)
+    uint64_t *patch_empty = patch_full + 2;             // [2] FIRST: patch buffer read by all producer warps
+    const uint32_t patch_base_u32 = smem_u32(extra + 2560);  // FIRST: 2 x float [PATCH_H][PATCH_S] input pixels
+    static_assert(!C::FIRST || (2560 + 2 * C::PATCH_BYTES <= C::XBASE && C::PATCH_S >= C::PATCH_W), "conv0 patches do not fit");
+    static_assert((4 * C::A_STAGES + 2 * C::B_STAGES + 4) * 8 + 4 <= 256, "barrier area");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -325,6 +332,10 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull_bar[b], 1);
             mbar_init(&tempty_bar[b], C::PAIR ? 8 : 4);  // PAIR: the epilogue warps of both CTAs release the leader
+            if (C::FIRST) {
+                mbar_init(&patch_full[b], 1);
+                mbar_init(&patch_empty[b], C::PRODUCERS / 32);
+            }
         }
         mbar_fence_init();
         tma_prefetch_desc(&map_w);
@@ -495,6 +506,49 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 commit(&tfull_bar[buf]);
             }
         }
+    } else if (warp == 3) {
+        // ===================== FIRST: conv0 patch staging.  The 20 x 36 input pixels a window needs (conv0 halo on top
+        // of the conv1 halo) go to one of two shared-memory patches, one item ahead of the producers, which used to do
+        // this themselves between two 256-thread named barriers per item (10 % of their time in barrier stalls, ncu).
+        if constexpr (C::FIRST) {
+            constexpr int NPX = C::PATCH_H * C::PATCH_W, NPL = (NPX + 31) / 32;
+            unsigned pit = 0;
+            for (int item = item_begin; item < item_end; ++item, ++pit) {
+                const int pb = pit & 1;
+                const int n = item / C::ITEMS_PER_IMAGE;
+                const int r = item - n * C::ITEMS_PER_IMAGE;
+                const int yb = r / C::ITEMS_X;
+                const int y0 = yb * 16, x0 = (r - yb * C::ITEMS_X) * 8 * C::NT;
+                uint32_t pv[NPL];
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) {
+                    const int idx = lane + 32 * i;
+                    const int py = idx / C::PATCH_W, px = idx - py * C::PATCH_W;
+                    const int gy = y0 - 2 + py, gx = x0 - 2 + px;
+                    uint32_t v = 0u;
+                    if (idx < NPX && n < p.nimg && gy >= 0 && gy < 128 && gx >= 0 && gx < 128) {
+                        const long long off = ((long long)n * 128 + gy) * 128 + gx;
+                        if (SRC == SRC_U8) v = __ldg((const uint8_t *)p.src + off);
+                        else v = __float_as_uint(__ldg((const float *)p.src + off));
+                    }
+                    pv[i] = v;
+                }
+                mbar_wait_bounded(&patch_empty[pb], ((pit >> 1) & 1u) ^ 1u);
+                const uint32_t dst = patch_base_u32 + (uint32_t)(pb * C::PATCH_BYTES);
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) {
+                    const int idx = lane + 32 * i;
+                    if (idx < NPX) {
+                        const int py = idx / C::PATCH_W, px = idx - py * C::PATCH_W;
+                        // ToTensor: uint8 -> float32, true division by 255 (latice/data_module.py:31)
+                        const float v = SRC == SRC_U8 ? (float)pv[i] / 255.0f : __uint_as_float(pv[i]);
+                        sts32(dst + (uint32_t)((py * C::PATCH_S + px) * 4), __float_as_uint(v));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&patch_full[pb]);
+            }
+        }
     } else if (warp >= 4 && warp < 8) {
         // ===================== epilogue
         const int quarter = warp & 3;
@@ -509,7 +563,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         // staging rows of this lane: pooled pixel / un-pooled pixel in the warp's TMA box ([n][y][x] order)
         const int prow = C::NI == 1 ? ((lane >> 4) * 4 + (xl >> 1)) : (im * 4 + (xl >> 1));
         const int urow = C::NI == 1 ? lane : (im * 16 + ((lane >> 4) & 1) * 8 + xl);
-        const uint32_t stg_u32 = smem_u32(extra + 8192) + (uint32_t)(quarter * C::NSB * C::WSTG);
+        const uint32_t stg_u32 = smem_u32(extra + C::XBASE) + (uint32_t)(quarter * C::NSB * C::WSTG);
         int sbuf = 0;
         float acc1[NCB][C::NI], acc2[NCB][C::NI];
 #pragma unroll
@@ -771,43 +825,13 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     wreg[tp][j] = make_float2(__ldg(p.w0 + tp * 32 + cg * 8 + 2 * j), __ldg(p.w0 + tp * 32 + cg * 8 + 2 * j + 1));
-            // the 20 x 36 input pixels of a window (conv0 halo on top of the conv1 halo) are fetched one item ahead
-            constexpr int NPV = (C::PATCH_H * C::PATCH_W + C::PRODUCERS - 1) / C::PRODUCERS;
-            uint32_t pv[NPV];  // raw pixel bits; converted when they are written to the patch, one item later
-            auto load_patch = [&](int item) {
-                int n, y0, x0;
-                decode(item, n, y0, x0);
-#pragma unroll
-                for (int i = 0; i < NPV; ++i) {
-                    const int idx = ptid + C::PRODUCERS * i;
-                    const int py = idx / C::PATCH_W, px = idx - py * C::PATCH_W;
-                    const int gy = y0 - 2 + py, gx = x0 - 2 + px;
-                    uint32_t v = 0u;
-                    if (idx < C::PATCH_H * C::PATCH_W && n < p.nimg && gy >= 0 && gy < 128 && gx >= 0 && gx < 128) {
-                        const long long off = ((long long)n * 128 + gy) * 128 + gx;
-                        if (SRC == SRC_U8) v = __ldg((const uint8_t *)p.src + off);
-                        else v = __float_as_uint(__ldg((const float *)p.src + off));
-                    }
-                    pv[i] = v;
-                }
-            };
-            if (item_begin < item_end) load_patch(item_begin);
             for (int item = item_begin; item < item_end; ++item, ++ait) {
                 int n, y0, x0;
                 decode(item, n, y0, x0);
                 update_table(n);
-                named_bar_sync(1, C::PRODUCERS);
-#pragma unroll
-                for (int i = 0; i < NPV; ++i)
-                    if (ptid + C::PRODUCERS * i < C::PATCH_H * C::PATCH_W) {
-                        // ToTensor: uint8 -> float32, true division by 255 (latice/data_module.py:31)
-                        const float v = SRC == SRC_U8 ? (float)pv[i] / 255.0f : __uint_as_float(pv[i]);
-                        const int idx = ptid + C::PRODUCERS * i;
-                        const int py = idx / C::PATCH_W, px = idx - py * C::PATCH_W;
-                        sts32(patch_u32 + (py * C::PATCH_S + px) * 4, __float_as_uint(v));
-                    }
-                named_bar_sync(1, C::PRODUCERS);
-                if (item + 1 < item_end) load_patch(item + 1);
+                const int pb = ait & 1;   // patch buffer of this item (staged by warp 3)
+                mbar_wait_bounded(&patch_full[pb], (ait >> 1) & 1u);
+                const uint32_t patch_u32 = patch_base_u32 + (uint32_t)(pb * C::PATCH_BYTES);
                 const int sa = ait % C::A_STAGES;
                 mbar_wait_bounded(&a_empty[sa], ((ait / C::A_STAGES) & 1u) ^ 1u);
                 const uint32_t stage_u32 = smem_base_u32 + sa * C::A_STAGE;
@@ -840,6 +864,8 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     }
                     store_chunk<C>(stage_u32, pos, cg, hi, lo);
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&patch_empty[pb]);   // this warp is done reading the patch
                 fence_proxy_async();
                 if (C::PAIR) {
                     __syncwarp();
