@@ -880,7 +880,9 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
             // stage and item boundaries (a stage = one K chunk of one window).
             constexpr int C8 = C::KC / 8;
             constexpr int UNITS = C::WIN_POS * C8;
-            constexpr int BATCH = 4;
+            // units per thread and batch.  1296 (block 2) and 1440 (blocks 3-7) units per stage are two batches of 768 with 3 per
+            // thread; with 4 the second batch ran 27-40 % full (measured: blocks 2/3 -6 %, block 5 -3 %)
+            constexpr int BATCH = (UNITS > 4 * C::PRODUCERS && UNITS <= 6 * C::PRODUCERS) ? 3 : 4;
             constexpr int NBATCH = (UNITS + C::PRODUCERS * BATCH - 1) / (C::PRODUCERS * BATCH);
             struct Cursor {
                 int item, cc, b;
