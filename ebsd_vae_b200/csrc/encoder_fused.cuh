@@ -367,7 +367,10 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     if (warp == 0) {
         // ===================== weight loads (TMA) + L2 prefetch of the windows the producers will read
         if (elect_one_sync()) {
-            constexpr int PF = 4;  // items ahead: the producers themselves run up to A_STAGES items ahead of the MMAs
+            // items ahead (the producers themselves run up to A_STAGES items ahead of the MMAs).  Measured on one box, whole
+            // bench step: PF = 8: 223 k patterns/s, 4: 225-229 k, 2: 233 k, 1: 231-234 k, 0: 224-226 k -- windows prefetched
+            // too early are evicted again by the blocks' own output stream before the producers read them
+            constexpr int PF = 2;
             auto prefetch_item = [&](int item) {
                 if (C::FIRST || item >= item_end || item >= p.nitems) return;
                 int n, y0, x0;
