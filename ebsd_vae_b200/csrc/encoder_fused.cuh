@@ -113,7 +113,12 @@ struct FusedCfg {
     static constexpr int TMEM_COLS = 512;
     static constexpr int SMEM_BYTES = 1024 + A_STAGES * A_STAGE + B_BYTES + EXTRA;
     static constexpr int THREADS = 512;
-    static constexpr int PRODUCERS = 256;                    // producer threads (warps 8..15)
+    // producer threads: warps 8..15, plus the otherwise idle warps 2 and 3 in the blocks that read a raw plane (in the
+    // front-end block warp 3 stages the conv0 patch and the channel-group mapping needs a multiple of four warps)
+#ifndef EBSD_EXTRA_PRODUCERS
+#define EBSD_EXTRA_PRODUCERS 1
+#endif
+    static constexpr int PRODUCERS = (FIRST || !EBSD_EXTRA_PRODUCERS) ? 256 : 320;
     static constexpr int ITEMS_X = NI == 1 ? W / (8 * NT) : 1;
     static constexpr int ITEMS_PER_IMAGE = NI == 1 ? (W / 16) * ITEMS_X : 1;   // NI == 2: one item = 2 images
     static_assert(2 * ACC_COLS <= TMEM_COLS, "TMEM budget");
@@ -509,7 +514,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 commit(&tfull_bar[buf]);
             }
         }
-    } else if (warp == 3) {
+    } else if (warp == 3 && C::FIRST) {
         // ===================== FIRST: conv0 patch staging.  The 20 x 36 input pixels a window needs (conv0 halo on top
         // of the conv1 halo) go to one of two shared-memory patches, one item ahead of the producers, which used to do
         // this themselves between two 256-thread named barriers per item (10 % of their time in barrier stalls, ncu).
@@ -776,9 +781,9 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         }
         flush();
         if (lane == 0) bulk_wait_all();  // the staging buffers must outlive the TMA reads; stores complete before exit
-    } else if (warp >= 8) {
+    } else if (warp >= 8 || (C::PRODUCERS > 256 && (warp == 2 || warp == 3))) {
         // ===================== producers: build the fp16 hi / lo window in shared memory
-        const int ptid = threadIdx.x - 256;
+        const int ptid = warp >= 8 ? (int)threadIdx.x - 256 : 256 + (int)threadIdx.x - 64;
         const uint32_t smem_base_u32 = smem_u32(smem);
         auto decode = [&](int item, int &n, int &y0, int &x0) {
             if (C::NI == 1) {
@@ -885,8 +890,9 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
             constexpr int UNITS = C::WIN_POS * C8;
             // units per thread and batch.  1296 (block 2) and 1440 (blocks 3-7) units per stage are two batches of 768 with 3 per
             // thread; with 4 the second batch ran 27-40 % full (measured: blocks 2/3 -6 %, block 5 -3 %)
-            constexpr int BATCH = (UNITS > 4 * C::PRODUCERS && UNITS <= 6 * C::PRODUCERS) ? 3 : 4;
-            constexpr int NBATCH = (UNITS + C::PRODUCERS * BATCH - 1) / (C::PRODUCERS * BATCH);
+            constexpr int NB3 = (UNITS + C::PRODUCERS * 3 - 1) / (C::PRODUCERS * 3), NB4 = (UNITS + C::PRODUCERS * 4 - 1) / (C::PRODUCERS * 4);
+            constexpr int BATCH = 3 * NB3 < 4 * NB4 ? 3 : 4;   // fewer (mostly empty) unit slots per stage
+            constexpr int NBATCH = BATCH == 3 ? NB3 : NB4;
             struct Cursor {
                 int item, cc, b;
             };
