@@ -22,7 +22,8 @@
 //
 // Warp roles (512 threads): warp 0 weight TMA, warp 1 MMA issuer, warp 2 TMEM allocator, warp 3 conv0 patch staging
 // (front-end block only), warps 4-7 epilogue
-// (TMEM lane quarter = warp & 3), warps 8-15 producers (two per scheduler: global-load and ALU latency overlap).
+// (TMEM lane quarter = warp & 3), warps 8-15 producers (two per scheduler: global-load and ALU latency overlap), joined
+// by warps 2 and 3 in the blocks that read a raw plane.
 #pragma once
 #include "encoder_mma.cuh"
 
