@@ -288,8 +288,7 @@ topk_kernel(const __grid_constant__ CUtensorMap dict_map, const TopkParams p) {
 __global__ void __launch_bounds__(kThreads) topk_merge_parts_kernel(const Entry *parts, int S, long long Q, int k,
                                                                     long long index_base, float *out_dot,
                                                                     long long *out_idx, float *out_dist) {
-    // one CTA per query: each warp merges a slice of the S*k entries (two coalesced 32-entry loads in flight), warp 0
-    // merges the eight lists
+    // one CTA per query: each warp merges a slice of the S*k entries, warp 0 merges the eight lists
     __shared__ Entry lists_s[kWarps][kListLen];
     const long long q = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -318,10 +317,13 @@ __global__ void __launch_bounds__(kThreads) topk_merge_parts_kernel(const Entry 
             warp_insert<int>(e_dot, e_idx, __shfl_sync(0xffffffffu, e.dot, src), __shfl_sync(0xffffffffu, e.idx, src), lane);
         }
     };
-    for (int base = warp * per_warp; base < t_end; base += 64) {
-        const Entry a = fetch(base + lane), b = fetch(base + 32 + lane);
-        offer(a);
-        offer(b);
+    // eight coalesced 32-entry loads in flight per round trip (per_warp is a multiple of 64; rounds of 256 entries)
+    for (int base = warp * per_warp; base < t_end; base += 256) {
+        Entry e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = fetch(base + 32 * j + lane);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) offer(e[j]);
     }
     lists_s[warp][lane].dot = e_dot;
     lists_s[warp][lane].idx = e_idx;
