@@ -49,20 +49,20 @@ SYMBOLS = {
     "ebsd_encoder_workspace_bytes": (_size_t, [_c_void_p, _i64]),
     "ebsd_encoder_forward": (_int, [_c_void_p, _c_void_p, _int, _i64, _c_void_p, _c_void_p, _c_void_p, _size_t,
                                     _c_void_p]),
-    "ebsd_debug_conv_layer": (_int, [_c_void_p, _int, _int, _c_void_p, _int, _c_void_p, _c_void_p, _c_void_p, _size_t,
-                                     _c_void_p]),
-    "ebsd_debug_set_flags": (None, [_int]),
-    "ebsd_debug_fused_layer": (_int, [_c_void_p, _int, _int, _c_void_p, _c_void_p, _int, _int, _c_void_p, _c_void_p,
-                                      _c_void_p]),
+    "ebsd_encoder_block": (_int, [_c_void_p, _int, _int, _c_void_p, _c_void_p, _int, _int, _c_void_p, _c_void_p,
+                                  _c_void_p]),
     "ebsd_normalize_rows": (_int, [_c_void_p, _i64, _int, _c_void_p]),
     "ebsd_topk_workspace_bytes": (_size_t, [_i64, _i64, _int]),
     "ebsd_topk": (_int, [_c_void_p, _i64, _i64, _c_void_p, _i64, _int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                          _size_t, _c_void_p]),
     "ebsd_topk_merge": (_int, [_c_void_p, _c_void_p, _int, _i64, _int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "ebsd_topk_pack": (_int, [_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p]),
+    "ebsd_topk_merge_packed": (_int, [_c_void_p, _int, _i64, _int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "ebsd_euler_to_quat": (_int, [_c_void_p, _i64, _c_void_p, _c_void_p]),
     "ebsd_ipf_color": (_int, [_c_void_p, _i64, _int, _c_void_p, _c_void_p]),
-    "ebsd_consensus": (_int, [_c_void_p, _i64, _c_void_p, _i64, _int, ctypes.c_double, _int, _int, _int, _int,
-                              _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "ebsd_consensus": (_int, [_c_void_p, _c_void_p, _i64, _i64, _c_void_p, _i64, _int, ctypes.c_double, _int, _int,
+                              _int, _int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                              _c_void_p]),
 }
 
 _lib = None

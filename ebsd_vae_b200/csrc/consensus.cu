@@ -143,7 +143,10 @@ __device__ void euler_zxz_deg(const Quat &q, double out[3]) {
 
 struct ConsensusParams {
     const double *quat_table;
+    const double *euler_table;   // nullable: [N,3] degrees as stored, gathered into cand_euler
+    double *cand_euler;          // nullable: [Q,k,3], NaN where the candidate slot is empty
     long long N;
+    long long index_base;        // global row of table row 0 (cand_idx holds global rows)
     const long long *cand_idx;
     long long Q;
     int k;
@@ -166,8 +169,24 @@ __global__ void __launch_bounds__(256) consensus_kernel(const ConsensusParams p)
     const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
 
     long long row = -1;
-    if (lane < p.k) row = p.cand_idx[q * p.k + lane];
+    if (lane < p.k) {
+        row = p.cand_idx[q * p.k + lane];
+        if (row >= 0) row -= p.index_base;
+    }
     const bool have = row >= 0 && row < p.N;
+    if (p.cand_euler && lane < p.k) {
+        // candidate_orientations of OrientationResult (chroma_db.py:283-289): the stored Euler triplets, bit for bit
+        double e0 = kNaN, e1 = kNaN, e2 = kNaN;
+        if (have && p.euler_table) {
+            e0 = p.euler_table[row * 3 + 0];
+            e1 = p.euler_table[row * 3 + 1];
+            e2 = p.euler_table[row * 3 + 2];
+        }
+        double *dst = p.cand_euler + (q * p.k + lane) * 3;
+        dst[0] = e0;
+        dst[1] = e1;
+        dst[2] = e2;
+    }
     Quat mine = {0, 0, 0, 1};
     if (have) {
         const double4 t = *(const double4 *)(p.quat_table + row * 4);
@@ -407,10 +426,11 @@ int ebsd_ipf_color(const double *euler_deg, int64_t n, int axis, uint8_t *rgb, v
     return EBSD_OK;
 }
 
-int ebsd_consensus(const double *quat_table, int64_t N, const int64_t *cand_idx, int64_t Q, int k, double threshold,
-                   int angle_unit, int min_required_matches, int max_iterations, int faiss_semantics,
-                   double *mean_quat, double *mean_euler_deg, uint8_t *success, uint64_t *similar_mask,
-                   int32_t *ref_iter, void *stream) {
+int ebsd_consensus(const double *quat_table, const double *euler_table, int64_t N, int64_t index_base,
+                   const int64_t *cand_idx, int64_t Q, int k, double threshold, int angle_unit,
+                   int min_required_matches, int max_iterations, int faiss_semantics, double *mean_quat,
+                   double *mean_euler_deg, uint8_t *success, uint64_t *similar_mask, int32_t *ref_iter,
+                   double *cand_euler_deg, void *stream) {
     int rc = check_device_arch();
     if (rc) return rc;
     EBSD_REQUIRE(k >= 1 && k <= EBSD_MAX_TOPK, "ebsd_consensus: k must be in [1,%d], got %d", EBSD_MAX_TOPK, k);
@@ -424,7 +444,10 @@ int ebsd_consensus(const double *quat_table, int64_t N, const int64_t *cand_idx,
     EBSD_REQUIRE(((uintptr_t)quat_table & 31) == 0, "ebsd_consensus: quat_table must be 32-byte aligned");
     ConsensusParams p;
     p.quat_table = quat_table;
+    p.euler_table = euler_table;
+    p.cand_euler = cand_euler_deg;
     p.N = N;
+    p.index_base = index_base;
     p.cand_idx = (const long long *)cand_idx;
     p.Q = Q;
     p.k = k;

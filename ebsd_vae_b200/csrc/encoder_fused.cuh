@@ -1,15 +1,29 @@
-// K1, third generation: one kernel per convolution block that
-//   (1) BUILDS its own tensor-core operand in shared memory: "producer" warps read the previous block's raw fp32
+// K1: one kernel per convolution block that
+//   (1) BUILDS its own tensor-core operands in shared memory: "producer" warps read the previous block's raw fp32
 //       output (or, for the first tensor-core block, the uint8 pattern itself and run conv0 on CUDA cores), apply
 //       InstanceNorm + LeakyReLU(0.02) (latice/model.py:93-98) with the plane statistics the previous block left
-//       behind, split the result into fp16 hi / lo and store it in the swizzled K-major layout tcgen05.mma reads;
-//   (2) runs the 3x3 convolution as nine row-SHIFTED views of that window (implicit GEMM, three-term fp16 split,
-//       fp32 accumulation in TMEM, see encoder_mma.cuh for the arithmetic);
+//       behind, and store the result in the swizzled K-major layouts tcgen05.mma reads (see "Arithmetic");
+//   (2) runs the 3x3 convolution as nine row-SHIFTED views of that window (implicit GEMM, fp32 accumulation in TMEM);
 //   (3) finishes in the epilogue warps: TMEM -> registers, plane statistics of the un-pooled output (sum, sum of
 //       squares, fp64 atomics), optional 2x2 max-pool with warp shuffles (pooling commutes with the increasing map
 //       x -> leaky((x-mean)*rstd), so it is applied to the raw values), raw fp32 NHWC store.
 // Nothing but the (pooled) raw output and 2 numbers per (image, channel) goes to memory between blocks: there are no
 // finisher kernels, no fp16 planes in HBM/L2 and no TMA window re-reads.
+//
+// Arithmetic.  The latents must match torch fp32 within 1e-3 relative; a single fp16 (or bf16 / tf32) product per MAC
+// misses that by 3-5x, the exact three-term fp16 split a_hi*w_hi + a_hi*w_lo + a_lo*w_hi costs
+// three tensor-core passes.  Here each MAC is ONE fp16 pass plus ONE fp8 pass (fp8 runs at twice the fp16 rate, so
+// two units of tensor time instead of three):
+//     a*w  ~=  fp16(a) * fp16(w)                                             kind::f16,    N = Cout, K = 16 per MMA
+//            + [ e4m3(a) , e4m3(4096 (a - fp16 a)) ] . [ e4m3(4096 s (w - fp16 w)) ; e4m3(s w) ] / (4096 s)
+//                                                                            kind::f8f6f4, N = Cout, K = 32 per MMA
+// The two correction products are first-order error terms (2^-12 relative to a*w), so the 2^-4 relative rounding of
+// their e4m3 operands leaves 2^-16 per product: measured 1.2e-4 relative on the latents through all ten blocks
+// (tests/test_gpu_encoder.py; tools/emulate_split.py is the CPU emulation the design was chosen with), against 6e-6
+// for the three-term split and 3e-3 for one fp16 pass.  s is a per-layer power of two that brings max|w| into
+// (64, 128].  The fp16 products accumulate in TMEM columns [0, Cout), the scaled fp8 products in [Cout, 2 Cout); the
+// epilogue adds them as main + corr / (4096 s).  Per (tap, K chunk) the operand bytes are what the three-term split
+// needed -- an fp16 window and an equally sized window of (a, residual) byte pairs; [w_fp16 ; w_fp8] weight rows.
 //
 // Tile geometry.  A tile is 128 output positions = 16 groups of 8 horizontally adjacent pixels.  A UMMA K-major
 // operand is 16 eight-row groups at a constant stride (SBO), and tools/probe_umma_desc.cu shows that stride may be
@@ -25,7 +39,8 @@
 // (TMEM lane quarter = warp & 3), warps 8-15 producers (two per scheduler: global-load and ALU latency overlap), joined
 // by warps 2 and 3 in the blocks that read a raw plane.
 #pragma once
-#include "encoder_mma.cuh"
+#include "encoder_aux.cuh"
+#include "tcgen05.cuh"
 
 namespace ebsd {
 
@@ -65,11 +80,11 @@ struct FusedCfg {
     static constexpr int KC = CIN < 64 ? CIN : 64;
     static constexpr int ROWB = KC * 2;
     static constexpr int NCHUNK = CIN / KC;
-    static constexpr int B_TILE = 2 * COUT * ROWB;           // [w_hi; w_lo] of one (tap, K chunk)
-    // PAIR: per (tap, K chunk) a CTA holds X = its half of [w_hi; w_lo] (COUT rows: rank 0 w_hi, rank 1 w_lo) for the
-    // hi-plane MMA (N = 2*COUT) and Y = its half of w_hi (COUT/2 rows) for the lo-plane MMA (N = COUT)
-    static constexpr int B_X = PAIR ? COUT * ROWB : B_TILE;
-    static constexpr int B_Y = PAIR ? (COUT / 2) * ROWB : 0;
+    static constexpr int B_TILE = 2 * COUT * ROWB;           // [w_fp16; w_fp8] of one (tap, K chunk)
+    // per (tap, K chunk) a CTA holds X = the fp16 rows and Y = the fp8 rows of the weights, COUT rows each -- or,
+    // PAIR, its half of either (COUT/2 rows: cta_group::2 splits the N rows of B between the two CTAs)
+    static constexpr int B_X = (PAIR ? COUT / 2 : COUT) * ROWB;
+    static constexpr int B_Y = B_X;
     static constexpr int B_CTA = B_X + B_Y;                  // weight bytes one CTA holds per (tap, K chunk)
     // all nine taps stay in shared memory when they fit next to two windows: the 32-channel blocks always, the
     // 64 -> 64 block only as a pair (108 KB per CTA) and with one tile per window
@@ -83,7 +98,7 @@ struct FusedCfg {
     static constexpr int SWMASK = ROWB == 128 ? 7 : 3;
     static constexpr int KSTEPS = KC / 16;
     static constexpr int A_PLANE = (WIN_POS * ROWB + 1023) / 1024 * 1024;
-    static constexpr int A_STAGE = 2 * A_PLANE;              // hi + lo
+    static constexpr int A_STAGE = 2 * A_PLANE;              // fp16 window + fp8 (value, residual) window
     // CTA PAIRS (tcgen05 cta_group::2, M = 256): each CTA builds the window of its own work item and holds HALF of
     // every weight tile; the leader issues one MMA stream for both.  25 % fewer weight bytes per SM and half the B
     // operand reads of the tensor core, which matters because the single-CTA blocks are shared-memory-bandwidth bound.
@@ -135,11 +150,19 @@ struct FusedParams {
     double inv_src_plane;    // 1 / number of pixels those sums run over
     const float *w0;         // FIRST: conv0 weights [tap][32] fp32
     double *sums;            // out: [nimg,COUT,2], must be zero on entry
+    float corr_scale;        // 1 / (4096 * weight scale): brings the fp8 correction sum to the scale of the fp16 sum
     int nimg;
     int nitems;
-    int dbg;                 // profiling switches (ebsd_debug_set_flags): 1 producers write nothing, 2 no MMAs,
+#ifdef EBSD_ROLE_PROFILE
+    int dbg;                 // role-profiling build only (tools/time_fused.py): 1 producers write nothing, 2 no MMAs,
                              // 4 epilogue does nothing but release TMEM, 8 no plane statistics, 16 no stores
+#endif
 };
+#ifdef EBSD_ROLE_PROFILE
+#define EBSD_DBG(p) ((p).dbg)
+#else
+#define EBSD_DBG(p) 0
+#endif
 
 template <int ROWB, int GROUP_ROWS>
 __device__ __forceinline__ uint64_t umma_smem_desc_g(uint32_t saddr) {
@@ -212,6 +235,15 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, u
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_f8_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrives on the barrier at the same offset in BOTH CTAs of the pair once the preceding MMAs have completed
 __device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -266,26 +298,30 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
     return v;
 }
 
-// y = leaky(x * scale + shift) split into fp16 hi / lo; eight values -> two 16-byte chunks.
+// y = leaky(x * scale + shift) as fp16 plus the fp8 (value, residual) pairs of the correction product; eight values ->
+// two 16-byte chunks (fp16 window: 8 halves; fp8 window: per channel pair the bytes a(k), a(k+1), res(k), res(k+1)).
 // The table holds one float4 (scale_a, scale_b, shift_a, shift_b) per channel PAIR, laid out [pair j = 0..3][8-channel
 // group] so that the eight lanes that handle the eight channel groups of one position read 128 contiguous bytes (no
 // bank conflicts): pair j of group c8 sits at tab + j * jstride + c8 * 16.  tab_u32 already includes c8 * 16.
 // Packed fp32 pairs (FFMA2 / FMUL2, sm_100) halve the issue slots of the arithmetic.
-__device__ __forceinline__ void norm_split_pair(float2 x, const float4 &tt, __half2 &h, __half2 &l) {
+__device__ __forceinline__ void norm_split_pair(float2 x, const float4 &tt, __half2 &h, uint32_t &q) {
     const float2 y = __ffma2_rn(x, make_float2(tt.x, tt.y), make_float2(tt.z, tt.w));
     const float2 z = __fmul2_rn(y, make_float2(0.02f, 0.02f));
     const float2 a = make_float2(fmaxf(y.x, z.x), fmaxf(y.y, z.y));  // LeakyReLU(0.02)
     h = __floats2half2_rn(a.x, a.y);
-    const float2 d = __ffma2_rn(__half22float2(h), make_float2(-1.f, -1.f), a);  // exact: a - hi
-    l = __floats2half2_rn(d.x, d.y);
+    // exact: (a - fp16 a) * 4096
+    const float2 d = __ffma2_rn(__half22float2(h), make_float2(-kResidualScale, -kResidualScale),
+                                __fmul2_rn(a, make_float2(kResidualScale, kResidualScale)));
+    q = pack_e4m3x2(a.x, a.y) | (pack_e4m3x2(d.x, d.y) << 16);
 }
 __device__ __forceinline__ void norm_split8(const float (&x)[8], uint32_t tab_u32, uint32_t jstride, uint4 &hi,
                                             uint4 &lo) {
-    __half2 h[4], l[4];
+    __half2 h[4];
+    uint32_t l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) norm_split_pair(make_float2(x[2 * j], x[2 * j + 1]), lds128(tab_u32 + j * jstride), h[j], l[j]);
     hi = *(const uint4 *)h;
-    lo = *(const uint4 *)l;
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 template <class C>
@@ -394,8 +430,8 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 tma_prefetch_l2_4d(&map_src, 0, x0, y0, n);
             };
             for (int j = 0; j < PF + (C::RESIDENT_B ? C::A_STAGES : 0); ++j) prefetch_item(item_begin + j);
-            // one weight tile: a whole [w_hi; w_lo] box, or (PAIR) this CTA's X and Y parts in boxes of COUT/2 rows,
-            // with the bytes of both CTAs credited to the leader's barrier
+            // one weight tile: a whole [w_fp16; w_fp8] box, or (PAIR) this CTA's halves of the two as boxes of COUT/2
+            // rows, with the bytes of both CTAs credited to the leader's barrier
             auto load_weights = [&](uint8_t *dst_ptr, int kb, uint64_t *bar) {
                 if (!C::PAIR) {
                     mbar_expect_tx(bar, C::B_TILE);
@@ -405,9 +441,8 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     const int row0 = kb * 2 * COUT;
                     const uint32_t dst = smem_u32(dst_ptr);
                     const uint32_t lbar = map_to_cta(smem_u32(bar), 0);
-                    tma_load_2d_pair(dst, &map_w, 0, row0 + (int)cta_rank * COUT, lbar);
-                    tma_load_2d_pair(dst + C::B_X / 2, &map_w, 0, row0 + (int)cta_rank * COUT + COUT / 2, lbar);
-                    tma_load_2d_pair(dst + C::B_X, &map_w, 0, row0 + (int)cta_rank * (COUT / 2), lbar);
+                    tma_load_2d_pair(dst, &map_w, 0, row0 + (int)cta_rank * (COUT / 2), lbar);
+                    tma_load_2d_pair(dst + C::B_X, &map_w, 0, row0 + COUT + (int)cta_rank * (COUT / 2), lbar);
                 }
             };
             if (C::RESIDENT_B) {
@@ -437,14 +472,20 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     } else if (warp == 1) {
         // ===================== MMA issuer (PAIR: the leader CTA issues for both)
         if (cta_rank == 0 && elect_one_sync()) {
-            // hi plane: N = 2*COUT against [w_hi; w_lo]; lo plane: N = COUT against w_hi.  PAIR: M = 256 (this CTA's
-            // window rows + the peer's) with the B rows split between the two CTAs (X / Y regions of the stage)
-            constexpr uint32_t idesc_hi = C::PAIR ? umma_idesc_f16_m256(2 * COUT) : umma_idesc_f16(2 * COUT);
-            constexpr uint32_t idesc_lo = C::PAIR ? umma_idesc_f16_m256(COUT) : umma_idesc_f16(COUT);
-            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-                if (p.dbg & 2) return;
-                if (C::PAIR) umma_f16_pair(d, da, db, idesc, acc);
-                else umma_f16(d, da, db, idesc, acc);
+            // fp16 window x fp16 weights (X region) -> columns [0, COUT) of the tile's accumulator; fp8 window x fp8
+            // weights (Y region) -> columns [COUT, 2 COUT).  N = COUT for both; the instruction descriptor is the same
+            // word for the two kinds (format code 0 = F16 / E4M3).  PAIR: M = 256 (this CTA's window rows + the
+            // peer's) with the B rows split between the two CTAs.
+            constexpr uint32_t idesc = C::PAIR ? umma_idesc_f16_m256(COUT) : umma_idesc_f16(COUT);
+            auto mma = [&](bool f8, uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+                if (EBSD_DBG(p) & 2) return;
+                if (f8) {
+                    if (C::PAIR) umma_f8_pair(d, da, db, idesc, acc);
+                    else umma_f8(d, da, db, idesc, acc);
+                } else {
+                    if (C::PAIR) umma_f16_pair(d, da, db, idesc, acc);
+                    else umma_f16(d, da, db, idesc, acc);
+                }
             };
             auto commit = [&](uint64_t *bar) {
                 if (C::PAIR) umma_commit_pair(bar);
@@ -455,13 +496,13 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 else mbar_wait_bounded(bar, parity);
             };
             // all MMAs of one plane for one tap: NT tiles x KSTEPS
-            auto tap_mmas = [&](uint32_t d_item, uint32_t win, uint32_t b_w, uint32_t idesc, bool first) {
+            auto tap_mmas = [&](bool f8, uint32_t d_item, uint32_t win, uint32_t b_w, bool first) {
 #pragma unroll
                 for (int t = 0; t < C::NT; ++t)
 #pragma unroll
                     for (int k = 0; k < C::KSTEPS; ++k)
-                        mma(d_item + t * 2 * COUT, umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win + t * 8 * C::ROWB + k * 32),
-                            umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), idesc, (first && k == 0) ? 0u : 1u);
+                        mma(f8, d_item + t * 2 * COUT, umma_smem_desc_g<C::ROWB, C::GSTRIDE>(win + t * 8 * C::ROWB + k * 32),
+                            umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), (first && k == 0) ? 0u : 1u);
             };
             if (C::RESIDENT_B) {
                 for (int kb = 0; kb < 9 * C::NCHUNK; ++kb) wait(&b_full[kb], 0);
@@ -481,20 +522,20 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     const uint32_t win_hi = smem_u32(smem + sa * C::A_STAGE);
                     const uint32_t win_lo = win_hi + C::A_PLANE;
                     if (C::RESIDENT_B) {
-                        // all hi-plane MMAs, then all lo-plane MMAs: two instruction-descriptor switches per window
+                        // all fp16 MMAs, then all fp8 MMAs: two kind switches per window
 #pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap) {
                             const int dy = tap / 3, dx = tap - dy * 3;
                             const uint32_t shift = (uint32_t)((dy * C::PITCH + dx) * C::ROWB);
                             const uint32_t b_w = smem_u32(smem_b + (tap * C::NCHUNK + cc) * C::B_CTA);
-                            tap_mmas(d_item, win_hi + shift, b_w, idesc_hi, (cc | tap) == 0);
+                            tap_mmas(false, d_item, win_hi + shift, b_w, (cc | tap) == 0);
                         }
 #pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap) {
                             const int dy = tap / 3, dx = tap - dy * 3;
                             const uint32_t shift = (uint32_t)((dy * C::PITCH + dx) * C::ROWB);
                             const uint32_t b_w = smem_u32(smem_b + (tap * C::NCHUNK + cc) * C::B_CTA);
-                            tap_mmas(d_item, win_lo + shift, b_w + (C::PAIR ? C::B_X : 0), idesc_lo, false);
+                            tap_mmas(true, d_item + COUT, win_lo + shift, b_w + C::B_X, (cc | tap) == 0);
                         }
                     } else {
 #pragma unroll 1
@@ -505,8 +546,8 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                             wait(&b_full[sb], (bit / C::B_STAGES) & 1u);
                             tc_fence_after();
                             const uint32_t b_w = smem_u32(smem_b + sb * C::B_CTA);
-                            tap_mmas(d_item, win_hi + shift, b_w, idesc_hi, (cc | tap) == 0);
-                            tap_mmas(d_item, win_lo + shift, b_w + (C::PAIR ? C::B_X : 0), idesc_lo, false);
+                            tap_mmas(false, d_item, win_hi + shift, b_w, (cc | tap) == 0);
+                            tap_mmas(true, d_item + COUT, win_lo + shift, b_w + C::B_X, (cc | tap) == 0);
                             commit(&b_empty[sb]);
                         }
                     }
@@ -638,7 +679,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 if (lane == 0) bulk_wait_read<0>();
                 __syncwarp();
 #pragma unroll 1
-                for (int hf = 0; hf < ((p.dbg & 4) ? 0 : 2); ++hf) {
+                for (int hf = 0; hf < ((EBSD_DBG(p) & 4) ? 0 : 2); ++hf) {
                     float z[32];  // [0,16): sums, [16,32): sums of squares of channels hf*16 + i over the item's tiles
 #pragma unroll
                     for (int i = 0; i < 32; ++i) z[i] = 0.f;
@@ -650,7 +691,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            v[i] = valid ? v[i] + w[i] : 0.f;
+                            v[i] = valid ? fmaf(w[i], p.corr_scale, v[i]) : 0.f;
                             z[i] += v[i];
                             z[16 + i] = fmaf(v[i], v[i], z[16 + i]);
                         }
@@ -677,12 +718,12 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                                make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])));
                         fence_proxy_async();
                         __syncwarp();
-                        if (lane == 0 && n < p.nimg && !(p.dbg & 16)) {
+                        if (lane == 0 && n < p.nimg && !(EBSD_DBG(p) & 16)) {
                             tma_store_4d(&map_out, stg, hf * 16, (x0 + 8 * t) >> 1, (y0 + 4 * quarter) >> 1, n);
                             bulk_commit();
                         }
                     }
-                    if (!(p.dbg & 8)) {
+                    if (!(EBSD_DBG(p) & 8)) {
                         // one 32-wide transposing reduction serves both quantities: lane c < 16 ends up with the sum
                         // of channel hf*16 + c, lane 16 + c with its sum of squares
                         const float red = warp_transpose_reduce32(z, lane);
@@ -692,7 +733,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 }
             } else {
 #pragma unroll 1
-            for (int t = 0; t < ((p.dbg & 4) ? 0 : C::NT); ++t) {
+            for (int t = 0; t < ((EBSD_DBG(p) & 4) ? 0 : C::NT); ++t) {
 #pragma unroll
                 for (int cb = 0; cb < NCB; ++cb) {
                     float v[32], w[32];
@@ -700,7 +741,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     tmem_ld32(t_row + t * 2 * COUT + COUT + cb * 32, w);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] + w[i] : 0.f;
+                    for (int i = 0; i < 32; ++i) v[i] = valid ? fmaf(w[i], p.corr_scale, v[i]) : 0.f;
                     // ---- store through shared memory: one TMA box per warp, block of 32 channels and tile
                     const uint32_t stg = stg_u32 + (uint32_t)(sbuf * C::WSTG);
                     if (lane == 0) bulk_wait_read<C::NSB - 1>();
@@ -737,7 +778,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0 && n < p.nimg && !(p.dbg & 16)) {
+                    if (lane == 0 && n < p.nimg && !(EBSD_DBG(p) & 16)) {
                         int cx, cy;
                         if (C::NI == 1) {
                             cx = POOL ? (x0 + 8 * t) >> 1 : x0 + 8 * t;
@@ -751,7 +792,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     }
                     sbuf = (sbuf + 1) % C::NSB;
                     // plane statistics of the un-pooled output
-                    if (p.dbg & 8) continue;
+                    if (EBSD_DBG(p) & 8) continue;
                     if (C::NI == 1) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) w[i] = v[i] * v[i];
@@ -783,7 +824,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         flush();
         if (lane == 0) bulk_wait_all();  // the staging buffers must outlive the TMA reads; stores complete before exit
     } else if (warp >= 8 || (C::PRODUCERS > 256 && (warp == 2 || warp == 3))) {
-        // ===================== producers: build the fp16 hi / lo window in shared memory
+        // ===================== producers: build the fp16 window and the fp8 (value, residual) window in shared memory
         const int ptid = warp >= 8 ? (int)threadIdx.x - 256 : 256 + (int)threadIdx.x - 64;
         const uint32_t smem_base_u32 = smem_u32(smem);
         auto decode = [&](int item, int &n, int &y0, int &x0) {
@@ -848,7 +889,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 #pragma unroll
                 for (int j = 0; j < 4; ++j) tt[j] = lds128(tab_u32 + (uint32_t)((j * (CIN / 8) + cg) * 16));
 #pragma unroll 2
-                for (int pos = phalf * 32 + lane; pos < ((p.dbg & 1) ? 0 : C::WIN_POS); pos += 64) {
+                for (int pos = phalf * 32 + lane; pos < ((EBSD_DBG(p) & 1) ? 0 : C::WIN_POS); pos += 64) {
                     const int wy = pos / C::PITCH, wx = pos - wy * C::PITCH;
                     const int y = y0 - 1 + wy, x = x0 - 1 + wx;
                     uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
@@ -865,11 +906,12 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) acc[j] = __ffma2_rn(vv, wreg[dy * 3 + dx][j], acc[j]);
                             }
-                        __half2 h[4], l[4];
+                        __half2 h[4];
+                        uint32_t l[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) norm_split_pair(acc[j], tt[j], h[j], l[j]);
                         hi = *(const uint4 *)h;
-                        lo = *(const uint4 *)l;
+                        lo = make_uint4(l[0], l[1], l[2], l[3]);
                     }
                     store_chunk<C>(stage_u32, pos, cg, hi, lo);
                 }
@@ -884,7 +926,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 }
             }
         } else {
-            // raw fp32 -> normalise -> LeakyReLU -> fp16 hi / lo.  One unit = 8 channels of one window position; the
+            // raw fp32 -> normalise -> LeakyReLU -> fp16 + fp8 pairs.  One unit = 8 channels of one window position; the
             // global loads of the next batch of units are in flight while the current batch is converted, across
             // stage and item boundaries (a stage = one K chunk of one window).
             constexpr int C8 = C::KC / 8;
@@ -974,7 +1016,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     mbar_wait_bounded(&a_empty[sa], ((ait / C::A_STAGES) & 1u) ^ 1u);
                     stage_u32 = smem_base_u32 + sa * C::A_STAGE;
                 }
-                if (!(p.dbg & 1)) consume(cur, bc, stage_u32);
+                if (!(EBSD_DBG(p) & 1)) consume(cur, bc, stage_u32);
                 if (cur.b == NBATCH - 1) {
                     fence_proxy_async();
                     if (C::PAIR) {

@@ -27,6 +27,16 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// e4m3 x e4m3 -> fp32, K = 32 per instruction (twice the fp16 rate); operands byte-packed in the same K-major layouts
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -110,7 +120,8 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
     constexpr uint64_t sbo = (8ull * SWB) >> 4;            // 8-row group stride
     return (uint64_t)((saddr & 0x3ffffu) >> 4) | (0ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
-// Instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, M = 128.
+// Instruction descriptor: fp16 x fp16 -> fp32 (kind::f16) or e4m3 x e4m3 -> fp32 (kind::f8f6f4: format code 0 is
+// E4M3 there), both operands K-major, M = 128.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
     return (1u << 4)                      // D format: F32
            | (0u << 7) | (0u << 10)       // A, B format: F16

@@ -484,7 +484,9 @@ __global__ void topk_merge_global_kernel(const float *dots, const long long *idx
     }
 }
 
-// x[i,:] /= ||x[i,:]||, canonical arithmetic (fma chain, IEEE sqrt and division).
+// x[i,:] /= ||x[i,:]||, bit for bit what FaissLatentVectorDatabase._l2_normalize (latice/index/faiss_db.py:109-113)
+// computes with numpy on float32 rows: rounded squares s_j, numpy's pairwise sum r_j = s_j + s_{j+8},
+// ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)), IEEE sqrt and division, zero norm -> 1 (tests/golden/l2_normalize.npz).
 __global__ void normalize_rows_kernel(float *x, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -492,14 +494,12 @@ __global__ void normalize_rows_kernel(float *x, long long n) {
     float4 v[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) v[c] = row[c];
-    float n2 = 0.f;
+    const float *e = (const float *)v;
+    float r[8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        n2 = fmaf(v[c].x, v[c].x, n2);
-        n2 = fmaf(v[c].y, v[c].y, n2);
-        n2 = fmaf(v[c].z, v[c].z, n2);
-        n2 = fmaf(v[c].w, v[c].w, n2);
-    }
+    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(__fmul_rn(e[j], e[j]), __fmul_rn(e[j + 8], e[j + 8]));
+    const float n2 = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                               __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
     float norm = __fsqrt_rn(n2);
     if (norm == 0.f) norm = 1.f;
 #pragma unroll
@@ -687,6 +687,7 @@ static bool screen_applies(long long N, long long Q, int k) {
     if (min_rows < 0) {
         const char *e = getenv("EBSD_TOPK_SCREEN_MIN_ROWS");
         min_rows = (e && atoll(e) > 0) ? atoll(e) : 65536;
+        if (min_rows < 8192) min_rows = 8192;   // stage A searches >= 4096 rows and stage B whole 256-row tiles
     }
     return screen_enabled() && k < kScrCap / 2 && N >= min_rows && Q >= 2048 && N < 0x7fffff00ll;
 }
@@ -742,13 +743,21 @@ static int make_pairs_map(CUtensorMap *map, const void *base, long long rows, in
     return EBSD_OK;
 }
 
+constexpr int kMaxDevices = 64;
+static int current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 template <int TQ>
 static int launch_topk(const CUtensorMap &map, const TopkParams &p, int sms, cudaStream_t st) {
     using S = Smem<TQ>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};   // function attributes are per device
+    const int dev = current_device_slot();
+    if (!configured[dev]) {
         EBSD_CUDA_TRY(cudaFuncSetAttribute(topk_kernel<TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::alloc));
-        configured = true;
+        configured[dev] = true;
     }
     const int n_items = p.n_qtiles * p.n_splits;
     const int slots = sms * (TQ <= 4 ? 2 : 1);  // resident CTAs
@@ -865,8 +874,14 @@ static int run_exact(const float *dict, long long N, long long index_base, const
 }
 
 static int run_screen(const float *dict, long long N, long long index_base, const float *queries, long long Q, int k,
-                      float *out_dot, long long *out_idx, float *out_dist, void *workspace, int sms, cudaStream_t st) {
+                      float *out_dot, long long *out_idx, float *out_dist, void *workspace, size_t workspace_bytes, int sms,
+                      cudaStream_t st) {
     const ScreenPlan pl = make_screen_plan(N, Q, sms);
+    // every chunk of a long query batch has its own plan (a short last chunk splits the seeding search more ways)
+    if (workspace == nullptr || workspace_bytes < pl.bytes) {
+        set_error("ebsd_topk: workspace too small (%zu < %zu)", workspace_bytes, pl.bytes);
+        return EBSD_ERR_WORKSPACE;
+    }
     uint8_t *ws = (uint8_t *)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
     __half *dpairs = (__half *)(ws + pl.off_dpairs);
     __half *qpairs = (__half *)(ws + pl.off_qpairs);
@@ -889,13 +904,15 @@ static int run_screen(const float *dict, long long N, long long index_base, cons
     //   C  screen of the remaining rows [n1, N), thr from B; the re-rank starts from B's list -> top-k of [0, N)
     // out_dot / out_idx carry the running exact lists between the stages (each kernel reads them before the next
     // one overwrites them: same stream).
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};   // function attributes are per device
+    const int dev = current_device_slot();
+    if (!configured[dev]) {
         EBSD_CUDA_TRY(cudaFuncSetAttribute(topk_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScrSmem));
-        configured = true;
+        configured[dev] = true;
     }
     const long long n1_tiles = ((N / 8 + kScrN - 1) / kScrN);
-    const long long n0 = screen_prefix_rows(n1_tiles * kScrN);   // N/64, at least 4096
+    long long n0 = screen_prefix_rows(n1_tiles * kScrN);   // N/64, at least 4096
+    if (n0 > N) n0 = N;
     if ((rc = run_exact(dict, n0, index_base, queries, Q, k, out_dot, out_idx, nullptr, ws + pl.off_parts, sms, st))) return rc;
     auto pass = [&](long long tile_begin, long long tile_end, int init_from_out) -> int {
         ScreenParams p;
@@ -930,6 +947,54 @@ static int run_screen(const float *dict, long long N, long long index_base, cons
     return pass(n1_tiles, total_tiles, 1);
 }
 
+// Workspace of the screen path for Q queries: ebsd_topk runs it in chunks of kScreenQueryChunk queries and every
+// chunk size has its own plan -- the largest of the (at most two) distinct plans counts, not the first chunk's.
+static size_t screen_workspace_bytes(long long N, long long Q, int sms) {
+    size_t need = 0;
+    if (Q >= kScreenQueryChunk) need = make_screen_plan(N, kScreenQueryChunk, sms).bytes;
+    const long long rem = Q % kScreenQueryChunk;
+    if (rem > 0) {
+        const size_t b = make_screen_plan(N, rem, sms).bytes;
+        if (b > need) need = b;
+    }
+    return need;
+}
+
+// ---- candidate exchange between shards: one 64-bit word per candidate = (dot bits << 32) | (global row + 1), so that
+// the per-shard lists travel in ONE collective; rows fit 32 bits for dictionaries below 2^32 - 1 rows.
+__global__ void pack_candidates_kernel(const float *__restrict__ dot, const long long *__restrict__ idx, long long n,
+                                       unsigned long long *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long r = idx[i];
+    out[i] = ((unsigned long long)__float_as_uint(dot[i]) << 32) | (unsigned long long)(unsigned)(r < 0 ? 0u : (unsigned)(r + 1));
+}
+
+// k-way merge of R packed lists [R,Q,k] (order: dot descending, global row ascending), one warp per query
+__global__ void topk_merge_packed_kernel(const unsigned long long *__restrict__ packed, int R, long long Q, int k,
+                                         float *out_dot, long long *out_idx, float *out_dist) {
+    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    float e_dot = -INFINITY;
+    long long e_idx = 0x7fffffffffffffffll;
+    for (int r = 0; r < R; ++r) {
+        const long long base = ((long long)r * Q + q) * k;
+        for (int j = 0; j < k; ++j) {
+            const unsigned long long w = packed[base + j];
+            const unsigned row1 = (unsigned)(w & 0xffffffffull);
+            if (row1 == 0u) break;
+            warp_insert<long long>(e_dot, e_idx, __uint_as_float((unsigned)(w >> 32)), (long long)row1 - 1, lane);
+        }
+    }
+    if (lane < k) {
+        const bool empty = e_idx == 0x7fffffffffffffffll;
+        out_dot[q * k + lane] = e_dot;
+        out_idx[q * k + lane] = empty ? -1ll : e_idx;
+        if (out_dist) out_dist[q * k + lane] = 1.0f - e_dot;
+    }
+}
+
 }  // namespace ebsd
 
 using namespace ebsd;
@@ -952,7 +1017,7 @@ int ebsd_normalize_rows(float *x, int64_t n, int d, void *stream) {
 
 size_t ebsd_topk_workspace_bytes(int64_t N, int64_t Q, int k) {
     if (N <= 0 || Q <= 0 || k <= 0) return 0;
-    if (screen_applies(N, Q, k)) return make_screen_plan(N, Q < kScreenQueryChunk ? Q : kScreenQueryChunk, sm_count()).bytes;
+    if (screen_applies(N, Q, k)) return screen_workspace_bytes(N, Q, sm_count());
     return exact_workspace_bytes(N, Q, k, sm_count());
 }
 
@@ -980,7 +1045,7 @@ int ebsd_topk(const float *dict, int64_t N, int64_t index_base, const float *que
 
     const int sms = sm_count();
     if (screen_applies(N, Q, k)) {
-        const size_t need_s = make_screen_plan(N, Q < kScreenQueryChunk ? Q : kScreenQueryChunk, sms).bytes;
+        const size_t need_s = screen_workspace_bytes(N, Q, sms);
         if (workspace == nullptr || workspace_bytes < need_s) {
             set_error("ebsd_topk: workspace too small (%zu < %zu)", workspace_bytes, need_s);
             return EBSD_ERR_WORKSPACE;
@@ -989,7 +1054,7 @@ int ebsd_topk(const float *dict, int64_t N, int64_t index_base, const float *que
         for (long long q0 = 0; q0 < Q; q0 += kScreenQueryChunk) {
             const long long qn = Q - q0 < kScreenQueryChunk ? Q - q0 : kScreenQueryChunk;
             if ((rc = run_screen(dict, N, index_base, queries + q0 * kD, qn, k, out_dot + q0 * k, (long long *)out_idx + q0 * k,
-                                 out_dist ? out_dist + q0 * k : nullptr, workspace, sms, st)))
+                                 out_dist ? out_dist + q0 * k : nullptr, workspace, workspace_bytes, sms, st)))
                 return rc;
         }
         return EBSD_OK;
@@ -1013,6 +1078,33 @@ int ebsd_topk_merge(const float *dots, const int64_t *idx, int R, int64_t Q, int
     const int wpb = 8;
     topk_merge_global_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
         dots, (const long long *)idx, R, Q, k, out_dot, (long long *)out_idx, out_dist);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}
+
+int ebsd_topk_pack(const float *dots, const int64_t *idx, int64_t n, uint64_t *packed, void *stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    EBSD_REQUIRE(n >= 0, "ebsd_topk_pack: negative size");
+    if (n == 0) return EBSD_OK;
+    EBSD_REQUIRE(dots && idx && packed, "ebsd_topk_pack: null pointer");
+    pack_candidates_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        dots, (const long long *)idx, n, (unsigned long long *)packed);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}
+
+int ebsd_topk_merge_packed(const uint64_t *packed, int R, int64_t Q, int k, float *out_dot, int64_t *out_idx,
+                           float *out_dist, void *stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    EBSD_REQUIRE(k >= 1 && k <= EBSD_MAX_TOPK, "ebsd_topk_merge_packed: k must be in [1,%d], got %d", EBSD_MAX_TOPK, k);
+    EBSD_REQUIRE(R >= 0 && Q >= 0, "ebsd_topk_merge_packed: negative size");
+    if (Q == 0) return EBSD_OK;
+    EBSD_REQUIRE(out_dot && out_idx && (R == 0 || packed), "ebsd_topk_merge_packed: null pointer");
+    const int wpb = 8;
+    topk_merge_packed_kernel<<<(unsigned)((Q + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        (const unsigned long long *)packed, R, Q, k, out_dot, (long long *)out_idx, out_dist);
     EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }

@@ -7,6 +7,10 @@
 //   quantise: (x * 255).astype(uint8) as numpy does it on x86-64 (torchvision to_pil_image): the product is
 //             rounded in the input's own precision, truncated toward zero to a 32-bit integer and the low byte kept;
 //             NaN and |x*255| >= 2^31 give 0 (cvttsd2si overflow pattern 0x80000000).  uint8 input is taken as is.
+//             The dictionary path (DPdataset.__getitem__, data_module.py:132) casts every frame to float64 FIRST, whatever
+//             the file holds -- uint8 / int16 / uint16 / int32 / float32 files included, so a stored 255 becomes
+//             65025 mod 256 = 1: src_dtype | EBSD_SRC_VIA_F64 does that cast here, per pixel, instead of a float64
+//             copy of the chunk on the host or the device.
 //   crop/pad: torchvision center_crop -- the host passes, per axis, the first source index, the first destination
 //             index and the length of the copied span (ebsd_vae_b200/transform.py:_axis_window); the rest is zero.
 #include "common.cuh"
@@ -31,8 +35,19 @@ struct CropParams {
     int sx, dx, lx;    // columns
 };
 
+template <int DTYPE>
+__device__ __forceinline__ double load_as_f64(const void *src, long long off) {
+    if (DTYPE == 0) return (double)((const uint8_t *)src)[off];
+    if (DTYPE == 1) return (double)((const float *)src)[off];
+    if (DTYPE == 2) return ((const double *)src)[off];
+    if (DTYPE == 3) return (double)((const int16_t *)src)[off];
+    if (DTYPE == 4) return (double)((const uint16_t *)src)[off];
+    if (DTYPE == 5) return (double)((const int32_t *)src)[off];
+    return (double)((const long long *)src)[off];
+}
+
 // one thread = four horizontally adjacent output pixels (one 32-bit store)
-template <int DTYPE>  // 0 = uint8, 1 = float32, 2 = float64
+template <int DTYPE, bool VIA_F64>  // EBSD_SRC_* (include/ebsd_b200.h)
 __global__ void __launch_bounds__(256) quantise_crop_kernel(const void *__restrict__ src, uint8_t *__restrict__ dst,
                                                             const CropParams p) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -51,7 +66,8 @@ __global__ void __launch_bounds__(256) quantise_crop_kernel(const void *__restri
             if (xx < 0 || xx >= p.lx) continue;
             const long long off = row + p.sx + xx;
             uint8_t v;
-            if (DTYPE == 0) v = ((const uint8_t *)src)[off];
+            if (VIA_F64) v = quantise_f64(load_as_f64<DTYPE>(src, off));
+            else if (DTYPE == 0) v = ((const uint8_t *)src)[off];
             else if (DTYPE == 1) v = quantise_f32(((const float *)src)[off]);
             else v = quantise_f64(((const double *)src)[off]);
             packed |= (uint32_t)v << (8 * j);
@@ -68,7 +84,9 @@ extern "C" int ebsd_quantize_crop(const void *src, int src_dtype, int64_t B, int
                                   int sx, int dx, int lx, uint8_t *dst, void *stream) {
     int rc = check_device_arch();
     if (rc) return rc;
-    EBSD_REQUIRE(src_dtype >= 0 && src_dtype <= 2, "ebsd_quantize_crop: bad dtype %d", src_dtype);
+    const bool via = (src_dtype & EBSD_SRC_VIA_F64) != 0;
+    const int code = src_dtype & ~EBSD_SRC_VIA_F64;
+    EBSD_REQUIRE(code >= 0 && code <= (via ? EBSD_SRC_I64 : EBSD_SRC_F64), "ebsd_quantize_crop: bad dtype %d", src_dtype);
     EBSD_REQUIRE(B >= 0 && H > 0 && W > 0, "ebsd_quantize_crop: bad shape");
     EBSD_REQUIRE(ly >= 0 && lx >= 0 && sy >= 0 && sx >= 0 && dy >= 0 && dx >= 0 && sy + ly <= H && sx + lx <= W &&
                      dy + ly <= 128 && dx + lx <= 128,
@@ -90,9 +108,21 @@ extern "C" int ebsd_quantize_crop(const void *src, int src_dtype, int64_t B, int
     const long long total = B * 128 * 32;
     const unsigned grid = (unsigned)((total + 255) / 256);
     cudaStream_t st = (cudaStream_t)stream;
-    if (src_dtype == 0) quantise_crop_kernel<0><<<grid, 256, 0, st>>>(src, dst, p);
-    else if (src_dtype == 1) quantise_crop_kernel<1><<<grid, 256, 0, st>>>(src, dst, p);
-    else quantise_crop_kernel<2><<<grid, 256, 0, st>>>(src, dst, p);
+    if (!via) {
+        if (code == 0) quantise_crop_kernel<0, false><<<grid, 256, 0, st>>>(src, dst, p);
+        else if (code == 1) quantise_crop_kernel<1, false><<<grid, 256, 0, st>>>(src, dst, p);
+        else quantise_crop_kernel<2, false><<<grid, 256, 0, st>>>(src, dst, p);
+    } else {
+        switch (code) {
+            case 0: quantise_crop_kernel<0, true><<<grid, 256, 0, st>>>(src, dst, p); break;
+            case 1: quantise_crop_kernel<1, true><<<grid, 256, 0, st>>>(src, dst, p); break;
+            case 2: quantise_crop_kernel<2, true><<<grid, 256, 0, st>>>(src, dst, p); break;
+            case 3: quantise_crop_kernel<3, true><<<grid, 256, 0, st>>>(src, dst, p); break;
+            case 4: quantise_crop_kernel<4, true><<<grid, 256, 0, st>>>(src, dst, p); break;
+            case 5: quantise_crop_kernel<5, true><<<grid, 256, 0, st>>>(src, dst, p); break;
+            default: quantise_crop_kernel<6, true><<<grid, 256, 0, st>>>(src, dst, p); break;
+        }
+    }
     EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }

@@ -172,27 +172,80 @@ class DiffractionPatternIndexer:
         logger.info(f"Adding {len(latent_vectors)} vectors to database")
         self.db.add_vectors(latent_vectors, orientations)
 
+    #: bytes of one pinned staging buffer of the streaming dictionary build (two are kept)
+    STAGING_BYTES = 128 << 20
+
     def _extract_latent_vectors_with_angles(self, pattern_path, angles_path):
         """Encode every pattern of the .npy file; returns (latents CUDA [N,16] f32, orientations [N,3] f64).
 
-        The reference's dataset casts each pattern to float64 before the transform (data_module.py:132), so
-        integer-typed files are scaled by 255 and wrap modulo 256 -- reproduced here.
+        Replaces the reference's DataLoader loop (dp_indexer.py:254-297, data_module.py:122-133) by a stream:
+        memory-mapped file -> two pinned staging buffers (filled by a few host threads) -> host-to-device copies on a
+        side stream -> ``ebsd_quantize_crop`` + encoder on the compute stream, so that reading chunk i+1 overlaps
+        encoding chunk i and frames cross PCIe once, in the file's own dtype.  The reference's dataset casts each
+        pattern to float64 before the transform (data_module.py:132), so integer-typed files are scaled by 255 and
+        wrap modulo 256 -- the kernel does that cast per pixel (``EBSD_SRC_VIA_F64``).
         """
         data = load_patterns(pattern_path)
         angles = parse_rotation_angles(angles_path)
         if len(angles) < len(data):
             raise ValueError(f"angle file has {len(angles)} rows for {len(data)} patterns")
-        outs = []
-        for a in range(0, len(data), self.ENCODE_CHUNK):
-            frames = np.array(data[a : a + self.ENCODE_CHUNK])  # writable copy of the (read-only) memory map slice
-            if frames.dtype not in (np.float64, np.float32, np.uint8, np.int16, np.int32, np.int64):
-                frames = frames.astype(np.float64)  # dtypes torch cannot carry: cast on the host like the reference
-            dev = torch.from_numpy(frames).to(self.device)
-            # DPdataset.__getitem__ casts to float64 before the transform (data_module.py:132); exact on the device too
-            u8 = transform_batch_device(dev.to(torch.float64), tuple(self.config.image_size))
-            outs.append(self.engine.encode(u8))
-        latents = torch.cat(outs) if outs else torch.empty((0, 16), dtype=torch.float32, device=self.device)
-        return latents, angles[: len(data)]
+        return self._encode_frames_streaming(data), angles[: len(data)]
+
+    _STREAM_DTYPES = (np.uint8, np.int16, np.uint16, np.int32, np.int64, np.float32, np.float64)
+
+    def _encode_frames_streaming(self, data: np.ndarray) -> torch.Tensor:
+        """[N,H,W] host array (typically a read-only memory map) -> mu [N,16] on the device, dataset semantics."""
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+
+        n = len(data)
+        mu = torch.empty((n, self.config.latent_dim), dtype=torch.float32, device=self.device)
+        if n == 0:
+            return mu
+        cast_on_host = data.dtype not in [np.dtype(t) for t in self._STREAM_DTYPES]   # e.g. float16, bool
+        np_dtype = np.dtype(np.float64) if cast_on_host else data.dtype
+        frame_bytes = int(np.prod(data.shape[1:])) * np_dtype.itemsize
+        chunk = int(max(2, min(self.ENCODE_CHUNK, self.STAGING_BYTES // max(frame_bytes, 1), n)))
+        chunk += chunk & 1
+        t_dtype = torch.from_numpy(np.empty(0, dtype=np_dtype)).dtype
+        shape = (chunk,) + tuple(data.shape[1:])
+        staging = [torch.empty(shape, dtype=t_dtype, pin_memory=True) for _ in range(2)]
+        staging_np = [s.numpy() for s in staging]
+        raw = [torch.empty(shape, dtype=t_dtype, device=self.device) for _ in range(2)]
+        compute = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        self._copy_stream.wait_stream(compute)   # `raw` was allocated on the compute stream
+        copied = [None, None]     # event: H2D of the chunk in staging[i] finished (the staging buffer may be refilled)
+        consumed = [None, None]   # event: quantise/crop of raw[i] finished (the device buffer may be overwritten)
+        workers = max(1, min(8, (os.cpu_count() or 2) - 1))
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            def fill(dst, src):
+                rows = len(src)
+                cuts = np.linspace(0, rows, min(workers, rows) + 1).astype(int)
+                list(pool.map(lambda ab: np.copyto(dst[ab[0]:ab[1]], src[ab[0]:ab[1]], casting="unsafe"),
+                              zip(cuts[:-1], cuts[1:])))
+
+            for i, a in enumerate(range(0, n, chunk)):
+                b = min(a + chunk, n)
+                s = i & 1
+                if copied[s] is not None:
+                    copied[s].synchronize()
+                fill(staging_np[s][: b - a], data[a:b])
+                with torch.cuda.stream(self._copy_stream):
+                    if consumed[s] is not None:
+                        self._copy_stream.wait_event(consumed[s])
+                    raw[s][: b - a].copy_(staging[s][: b - a], non_blocking=True)
+                    copied[s] = torch.cuda.Event()
+                    copied[s].record(self._copy_stream)
+                compute.wait_event(copied[s])
+                u8 = transform_batch_device(raw[s][: b - a], tuple(self.config.image_size), via_float64=True)
+                consumed[s] = torch.cuda.Event()
+                consumed[s].record(compute)
+                mu[a:b] = self.engine.encode(u8)
+        for s in range(2):   # the side stream's last reads of `raw` end before the buffers go back to the allocator
+            raw[s].record_stream(self._copy_stream)
+        return mu
 
     def encode_pattern(self, pattern) -> NDArray[np.float32]:
         """Encode a single diffraction pattern to latent space -> (16,) float32."""

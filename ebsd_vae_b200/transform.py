@@ -47,9 +47,13 @@ def transform_batch_u8(patterns: np.ndarray, image_size: tuple[int, int] = (128,
     return out
 
 
-def transform_batch_device(frames, image_size: tuple[int, int] = (128, 128)):
+def transform_batch_device(frames, image_size: tuple[int, int] = (128, 128), via_float64: bool = False):
     """Device version of :func:`transform_batch_u8`: CUDA tensor [B,H,W] (uint8 / float32 / float64) -> uint8
-    [B,128,128] on the same device, bit-identical to the host function (``ebsd_quantize_crop``)."""
+    [B,128,128] on the same device, bit-identical to the host function (``ebsd_quantize_crop``).
+
+    ``via_float64=True`` is the dictionary path: ``DPdataset.__getitem__`` casts every frame to float64 before the
+    transform (latice/data_module.py:132), so integer files are scaled by 255 and wrap modulo 256; the cast happens
+    per pixel inside the kernel and uint8 / int16 / uint16 / int32 / int64 / float32 / float64 frames are accepted."""
     import torch
 
     from . import _native
@@ -59,6 +63,8 @@ def transform_batch_device(frames, image_size: tuple[int, int] = (128, 128)):
     if frames.dim() != 3:
         raise ValueError(f"pic should be 2/3 dimensional. Got {frames.dim()} dimensions.")
     codes = {torch.uint8: 0, torch.float32: 1, torch.float64: 2}
+    if via_float64:
+        codes = {k: v | 16 for k, v in {**codes, torch.int16: 3, torch.uint16: 4, torch.int32: 5, torch.int64: 6}.items()}
     if frames.dtype not in codes:
         raise TypeError(f"Input type {frames.dtype} is not supported")
     frames = frames.contiguous()
@@ -87,10 +93,18 @@ def parse_rotation_angles(path: str | Path) -> np.ndarray:
         with open(path) as fh:
             lines = fh.readlines()[2:]
         rows = [[tok for tok in line.strip().split(" ") if tok] for line in lines]
-        if any(len(r) != 3 for r in rows):
-            bad = next(len(r) for r in rows if len(r) != 3)
-            raise ValueError(f"3 columns passed, passed data had {bad} columns")
-        return np.array(rows, dtype=np.float64).reshape(-1, 3)
+        # pd.DataFrame(rows, columns=[z1, x, z2]) (data_module.py:105-110): the LONGEST row must have three fields;
+        # shorter or empty rows (a trailing blank line) are padded with NaN
+        longest = max((len(r) for r in rows), default=3)
+        if longest != 3:
+            raise ValueError(f"3 columns passed, passed data had {longest} columns")
+        if all(len(r) == 3 for r in rows):   # the regular case: one C-level conversion
+            return np.array(rows, dtype=np.float64).reshape(-1, 3)
+        out = np.full((len(rows), 3), np.nan, dtype=np.float64)
+        for i, r in enumerate(rows):
+            for j, tok in enumerate(r):
+                out[i, j] = float(tok)
+        return out
     except FileNotFoundError:
         raise
     except Exception as exc:  # noqa: BLE001 - mirrors the reference's catch-all

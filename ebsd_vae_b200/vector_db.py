@@ -156,6 +156,13 @@ class LatentVectorDatabase:
         self._topk_ws: torch.Tensor | None = None
         self.index_base = 0                          # global row index of local row 0 (row-sharded use)
         logger.info("Created in-memory GPU latent dictionary '%s'", self.collection_name)
+        # both reference classes reopen a persisted store on construction (chroma_db.py:113-131 PersistentClient +
+        # get_collection; faiss_db.py:129-130 ``if self.npz_path.exists(): self.load()``)
+        if self.persist_directory is not None and self._reopen_on_init() and self.npz_path.exists():
+            self.load()
+
+    def _reopen_on_init(self) -> bool:
+        return True
 
     # ------------------------------------------------------------------ helpers
     def _dev(self) -> torch.device:
@@ -248,6 +255,8 @@ class LatentVectorDatabase:
     def npz_path(self) -> Path:
         """``<persist_directory>/<collection_name>.npz`` -- the role of Chroma's ``persist_directory``
         (chroma_db.py:113-117) and of the FAISS variant's single ``.npz`` file (faiss_db.py:125, 440-476)."""
+        if self.persist_directory is None:
+            raise ValueError("persist_directory is None: this dictionary is in-memory only (pass a path to save/load)")
         return Path(self.persist_directory) / f"{self.collection_name}.npz"
 
     def save(self, path: str | Path | None = None) -> Path:
@@ -329,10 +338,10 @@ class LatentVectorDatabase:
         dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
         if nq == 0:
             return dot, idx, dist
-        need = int(lib.ebsd_topk_workspace_bytes(self._count, nq, k))
-        if need and (self._topk_ws is None or self._topk_ws.numel() < need):
-            self._topk_ws = torch.empty(need, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev):   # the plan behind the workspace size depends on the CURRENT device's SM count
+            need = int(lib.ebsd_topk_workspace_bytes(self._count, nq, k))
+            if need and (self._topk_ws is None or self._topk_ws.numel() < need):
+                self._topk_ws = torch.empty(need, dtype=torch.uint8, device=dev)
             _native.check(
                 lib.ebsd_topk(
                     self._latents.data_ptr() if self._count else None, self._count, self.index_base,
@@ -343,37 +352,40 @@ class LatentVectorDatabase:
         return dot, idx, dist
 
     def _orientation_tables(self):
-        """(euler [N,3] f64, quat [N,4] f64) covering every global row referenced by search results."""
+        """(euler [N,3] f64, quat [N,4] f64, global row of table row 0) covering every row a search can return."""
+        if self._count == 0:
+            return None, None, self.index_base
         return self._eulers[: self._count], self._quats[: self._count], self.index_base
 
     def consensus_device(self, idx: torch.Tensor, orientation_threshold: float, min_required_matches: int,
                          max_iterations: int):
+        """Consensus of candidate lists idx [Q,k] (global rows, -1 = empty): one kernel launch, no eager glue.
+
+        Returns (mean_quat [Q,4], mean_euler [Q,3], success [Q] u8, similar_mask [Q] i64, ref_iter [Q] i32,
+        candidate Euler triplets [Q,k,3] -- NaN in empty slots), all on the device."""
         dev = self._dev()
         lib = _native.load()
         nq, k = idx.shape
         eulers, quats, base = self._orientation_tables()
-        if base:
-            idx = torch.where(idx >= 0, idx - base, idx)
         mean_q = torch.empty((nq, 4), dtype=torch.float64, device=dev)
         mean_e = torch.empty((nq, 3), dtype=torch.float64, device=dev)
         success = torch.empty((nq,), dtype=torch.uint8, device=dev)
         mask = torch.empty((nq,), dtype=torch.int64, device=dev)
         ref_it = torch.empty((nq,), dtype=torch.int32, device=dev)
+        cand = torch.empty((nq, k, 3), dtype=torch.float64, device=dev)
         faiss = self.config.mode == "faiss"
         if nq:
+            n_rows = 0 if quats is None else quats.shape[0]
             with torch.cuda.device(dev):
                 _native.check(
                     lib.ebsd_consensus(
-                        quats.data_ptr() if quats.shape[0] else None, quats.shape[0], idx.data_ptr(), nq, k,
-                        float(orientation_threshold),
+                        quats.data_ptr() if n_rows else None, eulers.data_ptr() if n_rows else None, n_rows, int(base),
+                        idx.data_ptr(), nq, k, float(orientation_threshold),
                         _native.ANGLE_DEGREES if faiss else _native.ANGLE_RADIANS, int(min_required_matches),
                         int(max_iterations), int(faiss), mean_q.data_ptr(), mean_e.data_ptr(), success.data_ptr(),
-                        mask.data_ptr(), ref_it.data_ptr(), self._stream(dev)),
+                        mask.data_ptr(), ref_it.data_ptr(), cand.data_ptr(), self._stream(dev)),
                     "ebsd_consensus",
                 )
-        cand = eulers[idx.clamp(min=0)] if eulers.shape[0] else torch.full((nq, k, 3), float("nan"),
-                                                                           dtype=torch.float64, device=dev)
-        cand = torch.where((idx >= 0)[..., None], cand, torch.full_like(cand, float("nan")))
         return mean_q, mean_e, success, mask, ref_it, cand
 
     # ------------------------------------------------------------------ reference API
@@ -396,7 +408,7 @@ class LatentVectorDatabase:
             eulers, _, base = self._orientation_tables()
             orient = eulers[torch.as_tensor(idx_h - base, device=eulers.device)].cpu().numpy() if len(idx_h) else \
                 np.zeros((0, 3))
-            out["distances"] = [[float(d) for d in dist_h]]
+            out["distances"] = [[float(d) for d in dist_h]]   # cosine distance 1 - cos, ascending (chroma_db.py:127-130)
             out["metadatas"] = [[
                 {"orientation_str": ",".join(map(str, o.tolist())), "phi1": float(o[0]), "Phi": float(o[1]),
                  "phi2": float(o[2])} for o in orient
@@ -422,24 +434,40 @@ class LatentVectorDatabase:
         if q_in.dim() == 1:
             q_in = q_in[None]
         q = self._prepare_queries(q_in)
-        _, idx, dist = self.search_device(q, k)
-        n_avail = self._global_count()
-        if self.config.mode == "chroma" and min(n_avail, k) < max_iterations and q.shape[0] > 0:
-            # the reference indexes orientations[iteration] unguarded (chroma_db.py:302-303)
-            raise IndexError(f"index {min(n_avail, k)} is out of bounds for axis 0 with size {min(n_avail, k)}")
+        dot, idx, dist = self._search_for_consensus(q, k)
         _, mean_e, success, mask, _, cand = self.consensus_device(idx, orientation_threshold, min_required_matches,
                                                                   max_iterations)
-        # one synchronisation for all result arrays: asynchronous copies into pinned staging, then a single wait
-        qv, idx_h, dist_h, cand_h, succ_h, mean_h, mask_h = _to_host(q_in.detach(), idx, dist, cand, success, mean_e, mask)
+        return self._finish_batch(q_in, dot, idx, dist, cand, success, mean_e, mask, max_iterations)
+
+    def _search_for_consensus(self, q_hat: torch.Tensor, k: int):
+        return self.search_device(q_hat, k)
+
+    def _finish_batch(self, q_in, dot, idx, dist, cand, success, mean_e, mask, max_iterations) -> OrientationResultBatch:
+        faiss = self.config.mode == "faiss"
+        # one synchronisation for all result arrays: asynchronous copies into pinned staging, then a single wait.
+        # FAISS semantics carry the inner products as ``distances`` (faiss_db.py:216-256, 281-300), Chroma the cosine
+        # distance 1 - cos.
+        qv, idx_h, dist_h, cand_h, succ_h, mean_h, mask_h = _to_host(q_in.detach(), idx, dot if faiss else dist, cand,
+                                                                     success, mean_e, mask)
+        succ_h = succ_h.astype(bool)
+        if not faiss and len(succ_h):
+            # The reference indexes orientations[iteration] unguarded (chroma_db.py:302-303) and leaves the loop on
+            # success (:324-326): a query raises IndexError only when every reference orientation it has failed and
+            # the next iteration would index past its candidates.  (FAISS clamps the loop instead, faiss_db.py:302.)
+            n_valid = (idx_h >= 0).sum(axis=1)
+            bad = np.flatnonzero(~succ_h & (n_valid < max_iterations))
+            if len(bad):
+                n = int(n_valid[bad[0]])
+                raise IndexError(f"index {n} is out of bounds for axis 0 with size {n}")
         return OrientationResultBatch(
             query_vectors=qv,
             indices=idx_h,
             distances=dist_h,
             candidate_orientations=cand_h,
-            success=succ_h.astype(bool),
+            success=succ_h,
             mean_orientations=mean_h,
             similar_masks=mask_h.astype(np.uint64),
-            faiss_mode=self.config.mode == "faiss",
+            faiss_mode=faiss,
         )
 
     def _global_count(self) -> int:

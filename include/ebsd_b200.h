@@ -38,6 +38,17 @@ extern "C" {
 #define EBSD_PATTERN_U8 0      /* uint8 [B,128,128], value k means k/255 (ToTensor, latice/data_module.py:31) */
 #define EBSD_PATTERN_F32 1     /* float32 [B,128,128], used as is (tensor inputs bypass the transform, dp_indexer.py:128-131) */
 
+/* ebsd_quantize_crop source types.  U8 / F32 / F64 alone: ToPILImage semantics (encode_pattern path).  Any type
+ * | EBSD_SRC_VIA_F64: the frame is cast to float64 first, as DPdataset.__getitem__ does (latice/data_module.py:132). */
+#define EBSD_SRC_U8 0
+#define EBSD_SRC_F32 1
+#define EBSD_SRC_F64 2
+#define EBSD_SRC_I16 3
+#define EBSD_SRC_U16 4
+#define EBSD_SRC_I32 5
+#define EBSD_SRC_I64 6
+#define EBSD_SRC_VIA_F64 16
+
 #define EBSD_ANGLE_RADIANS 0   /* Chroma path: threshold compared with radians (latice/index/chroma_db.py:307-310) */
 #define EBSD_ANGLE_DEGREES 1   /* FAISS path: np.degrees first (latice/index/faiss_db.py:308-313) */
 
@@ -51,9 +62,9 @@ uint64_t ebsd_launch_count(void);
  *   replaces create_default_transform (latice/data_module.py:17-33) as applied by DPdataset.__getitem__
  *   (data_module.py:122-133) and encode_pattern / encode_patterns_batch (latice/index/dp_indexer.py:124-126,
  *   150-163), up to the uint8 image (ToTensor's k/255 is applied inside the encoder).
- * src: [B,H,W] device array, src_dtype 0 = uint8 (copied), 1 = float32, 2 = float64 ((x*255).astype(uint8) with
- * numpy/x86 semantics: product rounded in the source precision, truncated toward zero, low byte kept; NaN and
- * |x*255| >= 2^31 give 0).  Rows [sy, sy+ly) of the source go to rows [dy, dy+ly) of the 128-row output, columns
+ * src: [B,H,W] device array, src_dtype EBSD_SRC_U8 (copied), _F32, _F64 ((x*255).astype(uint8) with numpy/x86
+ * semantics: product rounded in the source precision, truncated toward zero, low byte kept; NaN and
+ * |x*255| >= 2^31 give 0), or any EBSD_SRC_* | EBSD_SRC_VIA_F64 (cast to float64 first: the dataset path).  Rows [sy, sy+ly) of the source go to rows [dy, dy+ly) of the 128-row output, columns
  * likewise; everything else is zero (torchvision center_crop: see ebsd_vae_b200/transform.py:_axis_window).
  * dst: uint8 [B,128,128], 4-byte aligned.
  * ------------------------------------------------------------------------------------------- */
@@ -88,22 +99,14 @@ size_t ebsd_encoder_workspace_bytes(const ebsd_encoder *enc, int64_t B);
 int ebsd_encoder_forward(ebsd_encoder *enc, const void *patterns, int dtype, int64_t B, float *mu, float *logvar,
                          void *workspace, size_t workspace_bytes, void *stream);
 
-/* Test hook: run convolution `layer` (1..9) alone on finished activations act [nimg,H,W,Cin] fp32 NHWC and return the
- * raw (pre-InstanceNorm) output raw [nimg,H,W,Cout] fp32 NHWC plus the plane sums [nimg,Cout,2] (sum, sum of squares).
- * use_mma = 1: tcgen05 path (workspace >= nimg*H*W*Cin*4 + 256 bytes), 0: fp32 CUDA-core path. */
-int ebsd_debug_conv_layer(ebsd_encoder *enc, int layer, int use_mma, const float *act, int nimg, float *raw,
-                          double *sums, void *workspace, size_t workspace_bytes, void *stream);
-
-/* Test hook for the fused blocks (encoder_fused.cuh): run block `layer` (1..9) alone.
+/* One encoder block alone (block `layer` = 1..9 of latice/model.py:109-125; block 1 includes conv0): what the
+ * per-block parity tests and bench.py's per-block roofline table call.
  * layer 1: src = patterns [nimg,128,128] (dtype EBSD_PATTERN_*); src_sums [nimg,32,2] is scratch (conv0 statistics).
  * layers 2..9: src = raw fp32 NHWC [nimg,W,W,Cin] and src_sums [nimg,Cin,2] its plane sums over src_plane pixels;
  * the block applies InstanceNorm + LeakyReLU to src, convolves, and returns raw [nimg,Wo,Wo,Cout] (2x2 max-pooled
  * for layers 1,3,5,7,9) plus the plane sums [nimg,Cout,2] of the un-pooled output. */
-int ebsd_debug_fused_layer(ebsd_encoder *enc, int layer, int dtype, const void *src, double *src_sums, int src_plane,
-                           int nimg, float *raw, double *sums, void *stream);
-
-/* Profiling hook: switches parts of the shifted-window conv kernel off (results are then wrong). 0 = normal. */
-void ebsd_debug_set_flags(int flags);
+int ebsd_encoder_block(ebsd_encoder *enc, int layer, int dtype, const void *src, double *src_sums, int src_plane,
+                       int nimg, float *raw, double *sums, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Latent dictionary: exact cosine top-k
@@ -126,6 +129,12 @@ int ebsd_topk(const float *dict, int64_t N, int64_t index_base, const float *que
 int ebsd_topk_merge(const float *dots, const int64_t *idx, int R, int64_t Q, int k, float *out_dot,
                     int64_t *out_idx, float *out_dist, void *stream);
 
+/* The same exchange with one 64-bit word per candidate, (float bits of dot << 32) | (global row + 1) with 0 = empty
+ * slot, so that the per-shard lists cross NVLink in ONE collective (needs fewer than 2^32 - 1 dictionary rows). */
+int ebsd_topk_pack(const float *dots, const int64_t *idx, int64_t n, uint64_t *packed, void *stream);
+int ebsd_topk_merge_packed(const uint64_t *packed, int R, int64_t Q, int k, float *out_dot, int64_t *out_idx,
+                           float *out_dist, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Orientation consensus
  *   replaces find_best_orientation + _find_symmetry_equivalent_orientation
@@ -134,13 +143,17 @@ int ebsd_topk_merge(const float *dots, const int64_t *idx, int R, int64_t Q, int
  * ------------------------------------------------------------------------------------------- */
 /* euler_deg [n,3] float64 (phi1, Phi, phi2; scipy "zxz" extrinsic, degrees) -> quat [n,4] float64 (x,y,z,w). */
 int ebsd_euler_to_quat(const double *euler_deg, int64_t n, double *quat, void *stream);
-/* quat_table [N,4]: orientation of every dictionary row; cand_idx [Q,k]: global rows from ebsd_topk (-1 = empty).
+/* quat_table [N,4] (32-byte aligned) / euler_table [N,3] (nullable): orientation of dictionary rows index_base ..
+ * index_base + N - 1; cand_idx [Q,k]: global rows from ebsd_topk (-1 = empty).
  * Outputs per query: mean_quat [Q,4], mean_euler_deg [Q,3] (NaN when !success), success [Q],
- * similar_mask [Q] (bit i = candidate i within threshold in the last iteration run), ref_iter [Q]. */
-int ebsd_consensus(const double *quat_table, int64_t N, const int64_t *cand_idx, int64_t Q, int k, double threshold,
-                   int angle_unit, int min_required_matches, int max_iterations, int faiss_semantics,
-                   double *mean_quat, double *mean_euler_deg, uint8_t *success, uint64_t *similar_mask,
-                   int32_t *ref_iter, void *stream);
+ * similar_mask [Q] (bit i = candidate i within threshold in the last iteration run), ref_iter [Q], and (nullable)
+ * cand_euler_deg [Q,k,3] = the stored Euler triplets of the candidates (OrientationResult.candidate_orientations,
+ * chroma_db.py:283-289; NaN in empty slots). */
+int ebsd_consensus(const double *quat_table, const double *euler_table, int64_t N, int64_t index_base,
+                   const int64_t *cand_idx, int64_t Q, int k, double threshold, int angle_unit,
+                   int min_required_matches, int max_iterations, int faiss_semantics, double *mean_quat,
+                   double *mean_euler_deg, uint8_t *success, uint64_t *similar_mask, int32_t *ref_iter,
+                   double *cand_euler_deg, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * IPF colour key of orientations (orientation maps)

@@ -13,6 +13,11 @@ Fixtures written:
   consensus.npz       -- ``ChromaLatentVectorDatabase.find_best_orientation`` (latice/index/chroma_db.py:261-342)
                          and the FAISS twin (latice/index/faiss_db.py:258-372) on seeded candidate sets,
                          incl. the reference's own known-answer case (tests/index/test_chroma_db.py:306-382).
+  consensus_short.npz -- the Chroma class on candidate lists SHORTER than ``max_iterations``: the reference indexes
+                         ``orientations[iteration]`` unguarded (chroma_db.py:302-303) but leaves the loop on success
+                         (:324-326), so it raises IndexError only when every available reference failed.
+  l2_normalize.npz    -- ``FaissLatentVectorDatabase._l2_normalize`` (latice/index/faiss_db.py:109-113, pure numpy) on
+                         seeded float32 rows incl. a zero row: pins the normalisation leg of the search oracle.
   anglefile_sample.txt + angles_sample.npy -- a regenerated copy of the 625-row sample angle file and what the
                          reference parser (latice/data_module.py:87-116) returns for the original.
 """
@@ -186,6 +191,50 @@ def main() -> None:
         os.path.join(GOLDEN, "consensus.npz"), cand=cand, k=ks, params=params,
         **{f"{m}_{key}": v for m, o in out.items() for key, v in o.items()},
     )
+    # ---- consensus on lists shorter than max_iterations (lazy IndexError of the Chroma class)
+    rng = np.random.default_rng(77)
+    short = []
+    base = np.array([[30.0, 45.0, 60.0], [30.5, 45.2, 60.1], [120.0, 10.0, 200.0]])
+    for k_s in (1, 2, 3):
+        for thr_s in (0.05, 3.0):
+            for mrm_s in (1, 2, 3):
+                for mit_s in (2, 3, 5):
+                    short.append((base[:k_s] + rng.normal(scale=0.01, size=(k_s, 3)), thr_s, mrm_s, mit_s))
+    ns = len(short)
+    s_cand = np.full((ns, 3, 3), np.nan)
+    s_k = np.zeros(ns, dtype=np.int64)
+    s_params = np.zeros((ns, 3))
+    s_raised = np.zeros(ns, bool)
+    s_success = np.zeros(ns, bool)
+    s_mean = np.full((ns, 3), np.nan)
+    s_similar = np.zeros((ns, 3), bool)
+    for i, (c, thr_s, mrm_s, mit_s) in enumerate(short):
+        s_cand[i, : len(c)] = c
+        s_k[i] = len(c)
+        s_params[i] = (thr_s, mrm_s, mit_s)
+        try:
+            r = run_chroma(ref, c, thr_s, mrm_s, mit_s)
+        except IndexError:
+            s_raised[i] = True
+            continue
+        s_success[i] = r.success
+        if r.mean_orientation is not None:
+            s_mean[i] = r.mean_orientation
+        if r.similar_indices is not None:
+            s_similar[i, np.asarray(r.similar_indices, dtype=np.int64)] = True
+    assert s_raised.any() and (~s_raised).any()
+    np.savez_compressed(os.path.join(GOLDEN, "consensus_short.npz"), cand=s_cand, k=s_k, params=s_params,
+                        raised=s_raised, success=s_success, mean=s_mean, similar=s_similar)
+
+    # ---- the FAISS class's row normalisation (pure numpy, so it runs here although faiss itself is a stub)
+    rng = np.random.default_rng(2024)
+    rows = (rng.normal(size=(4096, 16)) * rng.uniform(1e-3, 1e3, size=(4096, 1))).astype(np.float32)
+    rows[17] = 0.0
+    fdb = faiss_db.FaissLatentVectorDatabase.__new__(faiss_db.FaissLatentVectorDatabase)
+    normed = fdb._l2_normalize(rows.copy())
+    assert normed.dtype == np.float32
+    np.savez_compressed(os.path.join(GOLDEN, "l2_normalize.npz"), rows=rows, normalized=normed)
+
     print("golden fixtures written to", GOLDEN, "cases:", n,
           "chroma success:", int(out["chroma"]["success"].sum()), "faiss success:", int(out["faiss"]["success"].sum()))
 

@@ -12,7 +12,10 @@
  * faiss-cpu 1.10.0 and chroma-hnswlib 0.7.6 (uv.lock) are third-party and not installable here,
  * and neither defines a summation order or a tie order, so the bit-exact contract is stated here:
  *
- *   n2    = fma-chain  sum_j x_j*x_j, j = 0..D-1 ascending, starting from 0.0f
+ *   n2    = numpy's float32 pairwise sum of the ROUNDED squares s_j = x_j*x_j (D = 16): r_j = s_j + s_{j+8},
+ *           n2 = ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7))  -- what np.linalg.norm(axis=1) computes inside
+ *           _l2_normalize; pinned BIT FOR BIT by tests/golden/l2_normalize.npz (the reference's own function);
+ *           other D: plain ascending sum of rounded squares
  *   norm  = sqrtf(n2) (IEEE, round-to-nearest);  norm == 0  ->  1
  *   xhat_j = x_j / norm                                  (IEEE division)
  *   dot   = fma-chain  sum_j qhat_j*dhat_j, j ascending, starting from 0.0f
@@ -23,8 +26,9 @@
  * north star ranks identically; the kernel and this oracle rank on q.d directly.
  * NaN dots compare false against everything and are never selected.
  *
- * "parity unpinned" with respect to faiss/hnswlib themselves; anchored by the float64
- * brute-force cross-check in tests/test_oracle_topk.py.
+ * The normalisation leg is pinned to the reference (golden above).  The inner-product search leg stays
+ * "parity unpinned" with respect to faiss/hnswlib themselves; it is anchored by the float64 brute-force and the
+ * scikit-learn NearestNeighbors(metric="cosine", algorithm="brute") cross-checks in tests/test_oracle_topk.py.
  *
  * Build: gcc -O2 -mfma -ffp-contract=off -pthread -shared -fPIC   (oracle/Makefile)
  */
@@ -39,10 +43,31 @@ static inline float dot_chain(const float *a, const float *b, int d) {
     return acc;
 }
 
+/* sum of squares exactly as numpy's float32 add.reduce over a contiguous row does it (pairwise_sum, n = 16 < 128:
+ * eight running sums, combined as a balanced tree); volatile keeps every operation a separate fp32 rounding */
+static float sumsq_numpy(const float *row, int d) {
+    if (d == 16) {
+        volatile float r[8];
+        for (int j = 0; j < 8; ++j) {
+            volatile float a = row[j] * row[j], b = row[j + 8] * row[j + 8];
+            r[j] = a + b;
+        }
+        volatile float p0 = r[0] + r[1], p1 = r[2] + r[3], p2 = r[4] + r[5], p3 = r[6] + r[7];
+        volatile float q0 = p0 + p1, q1 = p2 + p3;
+        return q0 + q1;
+    }
+    volatile float acc = 0.0f;
+    for (int j = 0; j < d; ++j) {
+        volatile float s = row[j] * row[j];
+        acc = acc + s;
+    }
+    return acc;
+}
+
 void ebsd_oracle_normalize_rows(float *x, int64_t n, int d) {
     for (int64_t i = 0; i < n; ++i) {
         float *row = x + i * d;
-        float norm = sqrtf(dot_chain(row, row, d));
+        float norm = sqrtf(sumsq_numpy(row, d));
         if (norm == 0.0f) norm = 1.0f;
         for (int j = 0; j < d; ++j) row[j] = row[j] / norm;
     }

@@ -76,3 +76,18 @@ def topk_merge(dots: np.ndarray, idx: np.ndarray):
     out_idx = np.empty((q, k), dtype=np.int64)
     _load().ebsd_oracle_topk_merge(_fp(dots), _ip(idx), r, q, k, _fp(out_dot), _ip(out_idx))
     return out_dot, out_idx
+
+
+def pack_candidates(dots: np.ndarray, idx: np.ndarray) -> np.ndarray:
+    """(dot f32, global row i64, -1 = empty) -> one int64 word per candidate: (float bits << 32) | (row + 1), the
+    exchange format of ebsd_topk_pack / ebsd_topk_merge_packed (include/ebsd_b200.h)."""
+    bits = np.ascontiguousarray(dots, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    row1 = np.where(idx < 0, 0, idx + 1).astype(np.uint64)
+    return ((bits << np.uint64(32)) | row1).view(np.int64)
+
+
+def unpack_candidates(packed: np.ndarray):
+    w = np.ascontiguousarray(packed).view(np.uint64)
+    dots = (w >> np.uint64(32)).astype(np.uint32).view(np.float32)
+    idx = (w & np.uint64(0xFFFFFFFF)).astype(np.int64) - 1
+    return dots, idx

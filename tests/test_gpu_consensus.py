@@ -89,3 +89,36 @@ def test_random_cases_match_numpy_oracle():
             if r.success:
                 assert _misorientation_deg(mean_e[j], r.mean_orientation) < 1e-6
                 assert int(ref_it[j]) == r.ref_iteration
+
+
+def test_index_error_is_lazy_like_the_reference(golden_dir):
+    """Candidate lists shorter than max_iterations: the reference raises IndexError only for a query whose every
+    available reference orientation failed (chroma_db.py:302-326); a query that succeeds earlier returns normally --
+    e.g. top_n=2, min_required_matches=1.  Outcomes of the unmodified Chroma class: tests/golden/consensus_short.npz."""
+    import ebsd_vae_b200 as E
+    g = np.load(os.path.join(golden_dir, "consensus_short.npz"))
+    assert g["raised"].any() and (~g["raised"]).any()
+    for i in range(len(g["k"])):
+        k = int(g["k"][i])
+        thr, mrm, mit = float(g["params"][i, 0]), int(g["params"][i, 1]), int(g["params"][i, 2])
+        db = E.LatentVectorDatabase()
+        lat = np.eye(16, dtype=np.float32)[:k] + 1.0     # distinct rows; the query below ranks them 0, 1, 2
+        lat[:, 0] += np.arange(k, 0, -1)
+        db.add_vectors(lat, g["cand"][i, :k])
+        query = lat[0]
+        if g["raised"][i]:
+            with pytest.raises(IndexError):
+                db.find_best_orientation(query, top_n=20, orientation_threshold=thr, min_required_matches=mrm,
+                                         max_iterations=mit)
+            continue
+        r = db.find_best_orientation(query, top_n=20, orientation_threshold=thr, min_required_matches=mrm,
+                                     max_iterations=mit)
+        np.testing.assert_array_equal(r.candidate_orientations, g["cand"][i, :k])
+        assert r.success == bool(g["success"][i]), i
+        assert sorted(r.similar_indices.tolist()) == np.where(g["similar"][i, :k])[0].tolist(), i
+        if r.success:
+            assert _misorientation_deg(r.mean_orientation, g["mean"][i]) < 1e-6
+        # the FAISS twin clamps the loop (faiss_db.py:302) and never raises
+    dbf = E.LatentVectorDatabase(E.LatentVectorDatabaseConfig(mode="faiss"))
+    dbf.add_vectors(np.eye(16, dtype=np.float32)[:1], g["cand"][0, :1])
+    assert dbf.find_best_orientation(np.eye(16, dtype=np.float32)[0], top_n=20, min_required_matches=3).success is False

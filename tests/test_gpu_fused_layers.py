@@ -38,9 +38,9 @@ def _run(eng, layer, dtype, src, src_sums, src_plane, nimg):
     ho = hw // 2 if pool else hw
     raw = torch.full((nimg, ho, ho, cout), float("nan"), dtype=torch.float32, device="cuda")
     sums = torch.zeros((nimg, cout, 2), dtype=torch.float64, device="cuda")
-    _native.check(lib.ebsd_debug_fused_layer(eng._handle, layer, dtype, src.data_ptr(), src_sums.data_ptr(), src_plane,
+    _native.check(lib.ebsd_encoder_block(eng._handle, layer, dtype, src.data_ptr(), src_sums.data_ptr(), src_plane,
                                              nimg, raw.data_ptr(), sums.data_ptr(),
-                                             torch.cuda.current_stream().cuda_stream), "ebsd_debug_fused_layer")
+                                             torch.cuda.current_stream().cuda_stream), "ebsd_encoder_block")
     torch.cuda.synchronize()
     return raw, sums
 

@@ -12,7 +12,7 @@ from oracle import topk_ref as T
 from oracle import transform_ref as X
 
 pytestmark = pytest.mark.gpu
-N_PAT = 96
+N_PAT = 625   # the whole sample angle file (625 orientations), as BASELINE configs[0]
 
 
 def _misorientation_deg(e1, e2):
@@ -149,6 +149,7 @@ def test_dictionary_persistence_round_trip(tmp_path):
     assert saved["orientations"].shape == (3000, 3) and saved["orientations"].dtype == np.float64
 
     db2 = E.LatentVectorDatabase(cfg)
+    assert db2.get_count() == 3000   # an existing store is reopened on construction (chroma_db.py:113-131, faiss_db.py:129)
     db2.load()
     assert db2.get_count() == 3000
     after = db2.find_best_orientations_batch(q, top_n=10, min_required_matches=3, orientation_threshold=3.0)
@@ -162,3 +163,24 @@ def test_dictionary_persistence_round_trip(tmp_path):
     assert not path.exists() and db2.get_count() == 0
     with pytest.raises(FileNotFoundError, match="NPZ file missing."):
         db2.load()
+
+
+def test_faiss_mode_reports_inner_products_as_distances():
+    """FaissLatentVectorDatabase carries the inner products in ``distances`` (faiss_db.py:216-256, 281-300), Chroma the
+    cosine distance; ``get_top_n_orientations`` sorts ascending on whatever it is given, in both reference classes."""
+    import ebsd_vae_b200 as E
+
+    rng = np.random.default_rng(8)
+    lat = rng.normal(size=(2000, 16)).astype(np.float32)
+    eul = rng.uniform(0, 360, size=(2000, 3))
+    out = {}
+    for mode in ("chroma", "faiss"):
+        db = E.LatentVectorDatabase(E.LatentVectorDatabaseConfig(mode=mode, persist_directory=None))
+        db.add_vectors(lat, eul)
+        out[mode] = db.find_best_orientation(lat[11], top_n=10, orientation_threshold=3.0, min_required_matches=3)
+    np.testing.assert_array_equal(out["chroma"].candidate_orientations, out["faiss"].candidate_orientations)
+    np.testing.assert_allclose(out["faiss"].distances, 1.0 - out["chroma"].distances, atol=1e-6)
+    assert out["faiss"].distances[0] > 0.999 and (np.diff(out["faiss"].distances) <= 0).all()
+    assert out["chroma"].distances[0] < 1e-3 and (np.diff(out["chroma"].distances) >= 0).all()
+    with pytest.raises(ValueError, match="persist_directory is None"):
+        db.save()

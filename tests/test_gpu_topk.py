@@ -44,6 +44,15 @@ def test_normalize_rows_bit_exact():
     np.testing.assert_array_equal(got, T.normalize_rows(d))
 
 
+def test_normalize_rows_equals_reference_l2_normalize(golden_dir):
+    """Bit for bit the output of the reference's own FaissLatentVectorDatabase._l2_normalize
+    (latice/index/faiss_db.py:109-113; fixture made by oracle/make_golden.py from the unmodified class)."""
+    import os
+    g = np.load(os.path.join(golden_dir, "l2_normalize.npz"))
+    db = _db(g["rows"])
+    np.testing.assert_array_equal(db._latents[: db.get_count()].cpu().numpy(), g["normalized"])
+
+
 @pytest.mark.parametrize("n,q,k,dup", [
     (625, 1, 10, 0.0), (625, 1, 20, 0.0), (1000, 5, 20, 0.01), (5000, 200, 10, 0.01), (127, 3, 10, 0.0),
     (128, 16, 10, 0.0), (129, 17, 32, 0.0), (7, 4, 10, 0.0), (100_000, 300, 10, 0.001), (33_333, 1000, 1, 0.01),
@@ -149,7 +158,6 @@ def test_tensor_core_screen_equals_exact_kernel_incl_overflow_fallback(n, q):
     canonical arithmetic.  Its lists must equal the CUDA-core kernel's bit for bit -- also for queries whose k-th best
     dot is shared by hundreds of duplicate rows (survivor buffers overflow -> exact scan of the range) -- and the
     sampled oracle check pins both to the restatement."""
-    import os
     g = torch.Generator(device="cuda").manual_seed(77)
     d = torch.randn((n, 16), generator=g, device="cuda")
     d[100_000:100_700] = d[5]                     # 700 exact copies of row 5
@@ -162,11 +170,7 @@ def test_tensor_core_screen_equals_exact_kernel_incl_overflow_fallback(n, q):
     qs[1] = d[6]
     qh = db._prepare_queries(qs)
     dot_s, idx_s, _ = db.search_device(qh, 10)                       # screen path (N >= 65 536, Q >= 2048)
-    os.environ["EBSD_TOPK_SCREEN_OFF_FOR_TEST"] = "1"
-    try:
-        dot_e, idx_e, _ = db.search_device(qh[:1000].contiguous(), 10)   # Q < 2048 -> CUDA-core kernel
-    finally:
-        del os.environ["EBSD_TOPK_SCREEN_OFF_FOR_TEST"]
+    dot_e, idx_e, _ = db.search_device(qh[:1000].contiguous(), 10)   # Q < 2048 -> CUDA-core kernel
     assert torch.equal(idx_s[:1000], idx_e) and torch.equal(dot_s[:1000], dot_e)
     assert idx_s[0].tolist() == [5] + list(range(100_000, 100_009))  # ties: lowest rows win
     assert idx_s[1].tolist()[:1] == [6] and set(idx_s[1].tolist()[1:]) <= set(range(300_000, 300_040))
@@ -191,3 +195,36 @@ def test_tensor_core_screen_other_k(k):
     odot, oidx = T.topk(dn, qh[:32].cpu().numpy(), k, index_base=7, nthreads=8)
     np.testing.assert_array_equal(idx_s[:32].cpu().numpy(), oidx)
     np.testing.assert_array_equal(dot_s[:32].cpu().numpy(), odot)
+
+
+def test_screen_workspace_covers_every_query_chunk():
+    """A long query batch runs through the screen in chunks of 131 072 queries and the short LAST chunk has its own
+    plan (it splits the seeding search more ways): N = 4.2 M rows, Q = 131 072 + 118 928 (a 500 x 500 map) once wrote
+    past a workspace sized for the first chunk only.  The guard bytes behind the workspace must stay untouched and the
+    lists of the last chunk must equal a separate search of those queries."""
+    import ebsd_vae_b200 as E
+    from ebsd_vae_b200 import _native
+    lib = _native.load()
+    n, q, k = 4_200_000, 131_072 + 118_928, 20
+    g = torch.Generator(device="cuda").manual_seed(3)
+    d = torch.randn((n, 16), generator=g, device="cuda")
+    db = E.LatentVectorDatabase()
+    db.add_vectors(d, torch.zeros((n, 3), dtype=torch.float64, device="cuda"))
+    qs = d[torch.randint(0, n, (q,), generator=g, device="cuda")] + 0.03 * torch.randn((q, 16), generator=g, device="cuda")
+    qh = db._prepare_queries(qs)
+    need = int(lib.ebsd_topk_workspace_bytes(n, q, k))
+    guard = 64 << 20
+    ws = torch.zeros(need + guard, dtype=torch.uint8, device="cuda")
+    ws[need:] = 0xA5
+    dot = torch.empty((q, k), dtype=torch.float32, device="cuda")
+    idx = torch.empty((q, k), dtype=torch.int64, device="cuda")
+    _native.check(lib.ebsd_topk(db._latents.data_ptr(), n, 0, qh.data_ptr(), q, k, dot.data_ptr(), idx.data_ptr(), None,
+                                ws.data_ptr(), need, torch.cuda.current_stream().cuda_stream), "ebsd_topk")
+    torch.cuda.synchronize()
+    assert bool((ws[need:] == 0xA5).all()), "ebsd_topk wrote past the workspace it asked for"
+    # one byte less must be refused, not overrun
+    assert lib.ebsd_topk(db._latents.data_ptr(), n, 0, qh.data_ptr(), q, k, dot.data_ptr(), idx.data_ptr(), None,
+                         ws.data_ptr(), need - 1, torch.cuda.current_stream().cuda_stream) == -4
+    tail = qh[131_072:131_072 + 1500].contiguous()                     # Q < 2048 -> CUDA-core kernel
+    dot_e, idx_e, _ = db.search_device(tail, k)
+    assert torch.equal(idx[131_072:131_072 + 1500], idx_e) and torch.equal(dot[131_072:131_072 + 1500], dot_e)

@@ -64,10 +64,22 @@ def test_angle_parser(golden_dir, tmp_path):
     np.testing.assert_array_equal(got, np.load(os.path.join(golden_dir, "angles_sample.npy")))
     with pytest.raises(FileNotFoundError):
         transform.parse_rotation_angles(tmp_path / "missing.txt")
-    bad = tmp_path / "bad.txt"
-    bad.write_text("eu\n2\n0 1 0\n0 1\n")
-    with pytest.raises(ValueError, match="Failed to parse rotation angles file"):
-        transform.parse_rotation_angles(bad)
+    # malformed files behave as pd.DataFrame(rows, columns=[z1, x, z2]).astype(float) does in the reference
+    # (latice/data_module.py:100-110): short / blank rows are NaN-padded, too long or non-numeric rows raise
+    pd = pytest.importorskip("pandas")
+    cases = {"short.txt": "eu\n2\n0 1 0\n0 1\n", "blank.txt": "eu\n2\n0  1 0\n\n", "long.txt": "eu\n2\n0 1 0 5\n0 1 0\n",
+             "allshort.txt": "eu\n2\n0 1\n0\n", "text.txt": "eu\n2\n0 a 0\n", "empty.txt": "eu\n2\n"}
+    for name, text in cases.items():
+        f = tmp_path / name
+        f.write_text(text)
+        rows = [[t for t in line.strip().split(" ") if t] for line in text.splitlines(keepends=True)[2:]]
+        try:
+            want = pd.DataFrame(rows, columns=["z1", "x", "z2"]).astype(float).to_numpy().reshape(-1, 3)
+        except Exception:
+            with pytest.raises(ValueError, match="Failed to parse rotation angles file"):
+                transform.parse_rotation_angles(f)
+            continue
+        np.testing.assert_array_equal(transform.parse_rotation_angles(f), want)
 
 
 def test_config_defaults_match_reference():

@@ -25,6 +25,35 @@ def test_normalize_rows():
     np.testing.assert_allclose(dn, ref, rtol=3e-7, atol=0)
 
 
+def test_normalize_rows_equals_reference_l2_normalize(golden_dir):
+    """The normalisation leg of the search oracle is pinned bit for bit to the reference's own
+    FaissLatentVectorDatabase._l2_normalize (latice/index/faiss_db.py:109-113, fixture from oracle/make_golden.py)."""
+    import os
+    g = np.load(os.path.join(golden_dir, "l2_normalize.npz"))
+    np.testing.assert_array_equal(T.normalize_rows(g["rows"]), g["normalized"])
+
+
+def test_topk_sets_agree_with_sklearn_brute_force_cosine():
+    """Independent cross-check of the search leg: scikit-learn's exact cosine k-NN returns the
+    same neighbour SETS, except where the k-th and (k+1)-th cosine are within fp32 rounding of each other."""
+    nn = __import__("pytest").importorskip("sklearn.neighbors")
+    d, q = _data(30000, 200, 11, dup=50)
+    dn, qn = T.normalize_rows(d), T.normalize_rows(q)
+    dots, idx = T.topk(dn, qn, 10)
+    sk = nn.NearestNeighbors(n_neighbors=10, metric="cosine", algorithm="brute").fit(dn.astype(np.float64))
+    dist, nbrs = sk.kneighbors(qn.astype(np.float64))
+    s = qn.astype(np.float64) @ dn.astype(np.float64).T
+    n_diff = 0
+    for i in range(len(q)):
+        a, b = set(idx[i].tolist()), set(nbrs[i].tolist())
+        if a != b:
+            n_diff += 1
+            for r in a ^ b:   # rows only one side lists tie with the k-th best
+                assert abs(s[i, r] - np.sort(s[i])[-10]) < 4e-7
+    assert n_diff <= 4
+    np.testing.assert_allclose(1.0 - dots, dist, atol=4e-7)
+
+
 def test_topk_agrees_with_float64_bruteforce_up_to_near_ties():
     d, q = _data(20000, 128, 1)
     dn, qn = T.normalize_rows(d), T.normalize_rows(q)

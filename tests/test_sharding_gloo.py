@@ -1,7 +1,7 @@
 """World-size-2 gloo test (CPU) of the row-sharded search plumbing in ebsd_vae_b200/sharding.py.
 
-The collectives (uneven all-gather of query latents, all-gather of per-shard candidates, slicing of the own
-queries) run for real over gloo; the per-shard search and the merge are done by the oracle here because the
+The collectives (uneven and even all-gather of query latents, exchange of the packed per-shard candidates so that a
+rank ends up with the lists of its own queries) run for real over gloo; the per-shard search and the merge are done by the oracle here because the
 kernels need a GPU.  Checked property: sharded search + merge == one search over the whole dictionary.
 """
 import os
@@ -47,12 +47,21 @@ def _worker(rank, world, port, out_dir):
         np.testing.assert_array_equal(q_glob.numpy(), q_all)
 
         dot, idx = T.topk(shard, q_glob.numpy(), 10, index_base=index_base)
-        sd, si = sharding.exchange_candidates(torch.from_numpy(dot), torch.from_numpy(idx), q_counts)
-        assert tuple(sd.shape) == (world, q_counts[rank], 10)
-        md, mi = T.topk_merge(sd.numpy(), si.numpy())
+        packed = torch.from_numpy(T.pack_candidates(dot, idx))
+        got = sharding.exchange_packed(packed, q_counts)
+        assert tuple(got.shape) == (world, q_counts[rank], 10)
+        sd, si = T.unpack_candidates(got.numpy())
+        md, mi = T.topk_merge(sd, si)
         wd, wi = T.topk(d_all, q_all[cuts_q[rank]:cuts_q[rank + 1]], 10)
         np.testing.assert_array_equal(mi, wi)
         np.testing.assert_array_equal(md, wd)
+
+        # equal counts (the data-parallel case) gather without padding
+        q_even = torch.from_numpy(q_all[rank * 16:(rank + 1) * 16])
+        np.testing.assert_array_equal(sharding.all_gather_rows(q_even, [16, 16]).numpy(), q_all[:32])
+        # a rank without rows still takes part
+        empty = sharding.all_gather_rows(torch.zeros((0 if rank == 0 else 3, 4)), [0, 3])
+        assert tuple(empty.shape) == (3, 4)
 
         # replicated orientation table
         eul = torch.arange(len(shard) * 3, dtype=torch.float64).reshape(-1, 3) + 10000 * rank

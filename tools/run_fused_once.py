@@ -25,7 +25,7 @@ raw = torch.empty((n, ho, ho, cout), device="cuda")
 sums = torch.zeros((n, cout, 2), dtype=torch.float64, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
 for _ in range(reps):
-    _native.check(lib.ebsd_debug_fused_layer(eng._handle, layer, 0, src.data_ptr(), src_sums.data_ptr(), hw * hw, n,
+    _native.check(lib.ebsd_encoder_block(eng._handle, layer, 0, src.data_ptr(), src_sums.data_ptr(), hw * hw, n,
                                              raw.data_ptr(), sums.data_ptr(), st), "dbg")
 torch.cuda.synchronize()
 print("done", float(raw.abs().sum()))

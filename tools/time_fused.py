@@ -1,4 +1,9 @@
-"""Time one fused block under the profiling switches: python tools/time_fused.py LAYER NIMG"""
+"""Time one fused block with roles switched off: python tools/time_fused.py LAYER NIMG
+
+Needs the role-profiling build of the library (the product build has no such switches):
+    make -C ebsd_vae_b200/csrc OUT=$PWD/ab_libs/libebsd_profile.so BUILD=build_profile EXTRA=-DEBSD_ROLE_PROFILE
+    EBSD_B200_LIB=ab_libs/libebsd_profile.so python tools/time_fused.py 1 1184
+"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -24,11 +29,11 @@ raw = torch.empty((n, ho, ho, cout), device="cuda")
 sums = torch.zeros((n, cout, 2), dtype=torch.float64, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
 def run():
-    _native.check(lib.ebsd_debug_fused_layer(eng._handle, layer, 0, src.data_ptr(), src_sums.data_ptr(), hw * hw, n,
+    _native.check(lib.ebsd_encoder_block(eng._handle, layer, 0, src.data_ptr(), src_sums.data_ptr(), hw * hw, n,
                                              raw.data_ptr(), sums.data_ptr(), st), "dbg")
 REPS = 10
 for flags in (0, 1, 2, 4, 8, 16, 1 | 2, 1 | 4, 2 | 4, 1 | 2 | 4):
-    lib.ebsd_debug_set_flags(flags)
+    lib.ebsd_profile_set_flags(flags)
     for _ in range(3): run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -36,4 +41,4 @@ for flags in (0, 1, 2, 4, 8, 16, 1 | 2, 1 | 4, 2 | 4, 1 | 2 | 4):
     for _ in range(REPS): run()
     e1.record(); torch.cuda.synchronize()
     print(f"layer {layer} n {n} flags {flags:2d}: {e0.elapsed_time(e1) / REPS * 1e3:8.1f} us per call" + (" (incl. conv0 stats)" if layer == 1 else ""))
-lib.ebsd_debug_set_flags(0)
+lib.ebsd_profile_set_flags(0)
