@@ -615,40 +615,48 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         const int urow = C::NI == 1 ? lane : (im * 16 + ((lane >> 4) & 1) * 8 + xl);
         const uint32_t stg_u32 = smem_u32(extra + C::XBASE) + (uint32_t)(quarter * C::NSB * C::WSTG);
         int sbuf = 0;
-        float acc1[NCB][C::NI], acc2[NCB][C::NI];
+        // Running plane sums in fp64: the per-tile fp32 partial sums are fixed by the tile, but WHICH tiles of an image a
+        // CTA handles depends on where the image sits in the batch -- fp32 running sums made equal patterns differ by
+        // ~1e-7 in their statistics, fp64 ones (and fp64 atomics) agree to the last bit in practice.
+        // The 128-channel blocks would need 16-32 more registers for them: they add every tile's sums to memory directly
+        // (TILE_FLUSH; 4-8x more fp64 reductions at the L2, still a few hundred per image).
+        constexpr bool TILE_FLUSH = NCB >= 4;
+        constexpr int NACC = TILE_FLUSH ? 1 : NCB;
+        double acc1[NACC][C::NI], acc2[NACC][C::NI];
 #pragma unroll
-        for (int cb = 0; cb < NCB; ++cb)
+        for (int cb = 0; cb < NACC; ++cb)
 #pragma unroll
-            for (int s = 0; s < C::NI; ++s) acc1[cb][s] = acc2[cb][s] = 0.f;
-        float accum_lo = 0.f, accum_hi = 0.f;  // ACCUM: lane c < 16: sum of channel c (lo) / 16 + c (hi); lanes >= 16: squares
+            for (int s = 0; s < C::NI; ++s) acc1[cb][s] = acc2[cb][s] = 0.0;
+        double accum_lo = 0.0, accum_hi = 0.0;  // ACCUM: lane c < 16: sum of channel c (lo) / 16 + c (hi); lanes >= 16: squares
         int cur_n = -1;
         auto flush = [&]() {
             if (C::ACCUM) {
                 if (cur_n >= 0 && cur_n < p.nimg) {
                     double *dst = p.sums + ((long long)cur_n * COUT + (lane & 15)) * 2 + (lane >> 4);
-                    atomicAdd(dst, (double)accum_lo);
-                    atomicAdd(dst + 32, (double)accum_hi);
+                    atomicAdd(dst, accum_lo);
+                    atomicAdd(dst + 32, accum_hi);
                 }
-                accum_lo = accum_hi = 0.f;
+                accum_lo = accum_hi = 0.0;
                 return;
             }
+            if (TILE_FLUSH) return;
             if (cur_n >= 0) {
 #pragma unroll
                 for (int s = 0; s < C::NI; ++s) {
                     if (cur_n + s < p.nimg) {
 #pragma unroll
-                        for (int cb = 0; cb < NCB; ++cb) {
+                        for (int cb = 0; cb < NACC; ++cb) {
                             double *dst = p.sums + ((long long)(cur_n + s) * COUT + cb * 32 + lane) * 2;
-                            atomicAdd(dst, (double)acc1[cb][s]);
-                            atomicAdd(dst + 1, (double)acc2[cb][s]);
+                            atomicAdd(dst, acc1[cb][s]);
+                            atomicAdd(dst + 1, acc2[cb][s]);
                         }
                     }
                 }
             }
 #pragma unroll
-            for (int cb = 0; cb < NCB; ++cb)
+            for (int cb = 0; cb < NACC; ++cb)
 #pragma unroll
-                for (int s = 0; s < C::NI; ++s) acc1[cb][s] = acc2[cb][s] = 0.f;
+                for (int s = 0; s < C::NI; ++s) acc1[cb][s] = acc2[cb][s] = 0.0;
         };
         int j = 0;
         for (int item = item_begin; item < item_end; ++item, ++j) {
@@ -727,8 +735,8 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                         // one 32-wide transposing reduction serves both quantities: lane c < 16 ends up with the sum
                         // of channel hf*16 + c, lane 16 + c with its sum of squares
                         const float red = warp_transpose_reduce32(z, lane);
-                        if (hf == 0) accum_lo += red;
-                        else accum_hi += red;
+                        if (hf == 0) accum_lo += (double)red;
+                        else accum_hi += (double)red;
                     }
                 }
             } else {
@@ -796,8 +804,17 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     if (C::NI == 1) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) w[i] = v[i] * v[i];
-                        acc1[cb][0] += warp_transpose_reduce32(v, lane);
-                        acc2[cb][0] += warp_transpose_reduce32(w, lane);
+                        const float t1 = warp_transpose_reduce32(v, lane), t2 = warp_transpose_reduce32(w, lane);
+                        if (TILE_FLUSH) {
+                            if (n < p.nimg) {
+                                double *dst = p.sums + ((long long)n * COUT + cb * 32 + lane) * 2;
+                                atomicAdd(dst, (double)t1);
+                                atomicAdd(dst + 1, (double)t2);
+                            }
+                        } else {
+                            acc1[TILE_FLUSH ? 0 : cb][0] += (double)t1;
+                            acc2[TILE_FLUSH ? 0 : cb][0] += (double)t2;
+                        }
                     } else {
 #pragma unroll
                         for (int s = 0; s < C::NI; ++s) {
@@ -807,8 +824,17 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                                 a[i] = im == s ? v[i] : 0.f;
                                 b[i] = a[i] * a[i];
                             }
-                            acc1[cb][s] += warp_transpose_reduce32(a, lane);
-                            acc2[cb][s] += warp_transpose_reduce32(b, lane);
+                            const float t1 = warp_transpose_reduce32(a, lane), t2 = warp_transpose_reduce32(b, lane);
+                            if (TILE_FLUSH) {
+                                if (n + s < p.nimg) {
+                                    double *dst = p.sums + ((long long)(n + s) * COUT + cb * 32 + lane) * 2;
+                                    atomicAdd(dst, (double)t1);
+                                    atomicAdd(dst + 1, (double)t2);
+                                }
+                            } else {
+                                acc1[TILE_FLUSH ? 0 : cb][s] += (double)t1;
+                                acc2[TILE_FLUSH ? 0 : cb][s] += (double)t2;
+                            }
                         }
                     }
                 }

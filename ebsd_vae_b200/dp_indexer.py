@@ -185,11 +185,17 @@ class DiffractionPatternIndexer:
         pattern to float64 before the transform (data_module.py:132), so integer-typed files are scaled by 255 and
         wrap modulo 256 -- the kernel does that cast per pixel (``EBSD_SRC_VIA_F64``).
         """
+        from concurrent.futures import ThreadPoolExecutor
+
         data = load_patterns(pattern_path)
-        angles = parse_rotation_angles(angles_path)
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            # the angle file (text, ~1 us per row in Python) is parsed while the GPU encodes
+            angles_job = pool.submit(parse_rotation_angles, angles_path)
+            latents = self._encode_frames_streaming(data)
+            angles = angles_job.result()
         if len(angles) < len(data):
             raise ValueError(f"angle file has {len(angles)} rows for {len(data)} patterns")
-        return self._encode_frames_streaming(data), angles[: len(data)]
+        return latents, angles[: len(data)]
 
     _STREAM_DTYPES = (np.uint8, np.int16, np.uint16, np.int32, np.int64, np.float32, np.float64)
 
@@ -209,7 +215,11 @@ class DiffractionPatternIndexer:
         chunk += chunk & 1
         t_dtype = torch.from_numpy(np.empty(0, dtype=np_dtype)).dtype
         shape = (chunk,) + tuple(data.shape[1:])
-        staging = [torch.empty(shape, dtype=t_dtype, pin_memory=True) for _ in range(2)]
+        key = (shape, t_dtype)
+        if getattr(self, "_staging_key", None) != key:   # pinned allocations are slow (tens of ms): keep them
+            self._staging = [torch.empty(shape, dtype=t_dtype, pin_memory=True) for _ in range(2)]
+            self._staging_key = key
+        staging = self._staging
         staging_np = [s.numpy() for s in staging]
         raw = [torch.empty(shape, dtype=t_dtype, device=self.device) for _ in range(2)]
         compute = torch.cuda.current_stream(self.device)
@@ -243,8 +253,10 @@ class DiffractionPatternIndexer:
                 consumed[s] = torch.cuda.Event()
                 consumed[s].record(compute)
                 mu[a:b] = self.engine.encode(u8)
-        for s in range(2):   # the side stream's last reads of `raw` end before the buffers go back to the allocator
+        for s in range(2):   # the side stream's last writes of `raw` end before the buffers go back to the allocator
             raw[s].record_stream(self._copy_stream)
+            if copied[s] is not None:
+                copied[s].synchronize()   # the cached staging buffers may be refilled by the next call
         return mu
 
     def encode_pattern(self, pattern) -> NDArray[np.float32]:

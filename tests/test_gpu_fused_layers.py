@@ -54,7 +54,9 @@ def _check(layer, nimg, raw, sums, want_conv, pool):
     scale = want_conv.abs().max().item()
     err = (got - want).abs().max().item() / scale
     print(f"fused layer {layer} nimg {nimg}: max err / max |y| = {err:.3e}")
-    assert err < 2e-5
+    # one fp16 pass + one e4m3 pass of first-order corrections: ~2^-16 per product (a single fp16 pass gives ~5e-4 here,
+    # the three-term fp16 split of round 1 gave ~2e-6)
+    assert err < 5e-5   # measured 0.8e-5 .. 1.5e-5
     s1 = want_conv.sum(dim=(2, 3))
     s2 = (want_conv * want_conv).sum(dim=(2, 3))
     np.testing.assert_allclose(sums[:, :, 0].cpu().numpy(), s1.numpy(), rtol=0, atol=2e-5 * scale * hw * hw)
