@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "encoder_fused.cuh"
+#include "encoder_front.cuh"
 
 namespace ebsd {
 
@@ -30,6 +31,8 @@ struct ebsd_encoder {
     uint16_t *w_fused[EBSD_N_CONV];  // packed [w_fp16; w_fp8] rows of blocks 1..9 (encoder_aux.cuh)
     float corr_scale[EBSD_N_CONV];   // 1 / (4096 * weight scale) of the fp8 correction sum
     CUtensorMap w_map[EBSD_N_CONV];  // box = the slice one CTA fetches per (tap, K chunk)
+    uint8_t *w_front;             // shared-memory image of the front end's weights (encoder_front.cuh)
+    float c0_inv_scale;           // 1 / s0 of the front end's pre-scaled conv0 weights
     float *wh;                    // [32][2048] permuted heads
     float *bh;                    // [32]
 };
@@ -233,11 +236,67 @@ int launch_fused(const ebsd_encoder *enc, int layer, const void *src, const doub
     return EBSD_OK;
 }
 
+// uint8 patterns [nimg,128,128] as (x, y, n); box = the 20 x 48 pixel patch of one front-end work item, OOB = 0
+int make_pattern_map(CUtensorMap *map, const void *base, int nimg) {
+    tensormap_encode_fn encode = get_tensormap_encode();
+    if (!encode) {
+        set_error("encoder: cuTensorMapEncodeTiled entry point not available");
+        return EBSD_ERR_CUDA;
+    }
+    const cuuint64_t gdim[3] = {128, 128, (cuuint64_t)nimg};
+    const cuuint64_t gstride[2] = {128, 128 * 128};
+    const cuuint32_t box[3] = {(cuuint32_t)FrontCfg::PATCH_W, (cuuint32_t)FrontCfg::PATCH_H, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)base, gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("encoder: cuTensorMapEncodeTiled(patterns) failed with %d", (int)cr);
+        return EBSD_ERR_CUDA;
+    }
+    return EBSD_OK;
+}
+
+// Block 1 for 16-byte aligned uint8 patterns: conv0 and conv1 on the tensor cores (encoder_front.cuh)
+int launch_front(const ebsd_encoder *enc, const void *pats, const double *sums0, float *raw, double *sums, int nimg,
+                 cudaStream_t st) {
+    using C = FrontCfg;
+    static bool configured[kMaxDevices] = {};
+    EBSD_REQUIRE(enc->device >= 0 && enc->device < kMaxDevices, "encoder: device index %d out of range", enc->device);
+    if (!configured[enc->device]) {
+        EBSD_CUDA_TRY(cudaFuncSetAttribute(front_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured[enc->device] = true;
+    }
+    CUtensorMap map_pat, map_out;
+    int rc;
+    if ((rc = make_pattern_map(&map_pat, pats, nimg))) return rc;
+    if ((rc = make_out_map(&map_out, raw, 32, 64, nimg, 4, 2, 1, 16))) return rc;
+    FrontParams p;
+    p.sums0 = sums0;
+    p.weights = enc->w_front;
+    p.sums = sums;
+    p.c0_inv_scale = enc->c0_inv_scale;
+    p.corr_scale = enc->corr_scale[1];
+    p.nimg = nimg;
+    p.nitems = nimg * C::ITEMS_PER_IMAGE;
+#ifdef EBSD_DEBUG_NOTRAP
+    p.dbg = getenv("EBSD_FRONT_DBG") ? atoi(getenv("EBSD_FRONT_DBG")) : 0;
+#endif
+    const int sms = sm_count();
+    const int per = (p.nitems + sms - 1) / sms;
+    const int grid = (p.nitems + per - 1) / per;
+    front_u8_kernel<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map_pat, map_out, p);
+    EBSD_LAUNCH_CHECK();
+    return EBSD_OK;
+}
+
 // src: layer 1 -> patterns (dtype), layers 2..9 -> raw output of layer-1 ... ; sums must be zeroed by the caller
 int fused_dispatch(const ebsd_encoder *enc, int layer, int dtype, const void *src, const double *src_sums,
                    int src_plane, float *raw, double *sums, int nimg, cudaStream_t st) {
     switch (layer) {
         case 1:
+            if (dtype == EBSD_PATTERN_U8 && ((uintptr_t)src & 15) == 0 && !getenv("EBSD_FRONT_LEGACY"))
+                return launch_front(enc, src, src_sums, raw, sums, nimg, st);
             if (dtype == EBSD_PATTERN_U8)
                 return launch_fused<32, 32, 128, SRC_U8, true>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, st);
             return launch_fused<32, 32, 128, SRC_F32, true>(enc, layer, src, src_sums, src_plane, raw, sums, nimg, st);
@@ -328,12 +387,12 @@ int ebsd_encoder_create(ebsd_encoder **out, const ebsd_weights *w, int device, v
     }
     float *d_absmax = nullptr;
     EBSD_CUDA_TRY(cudaMalloc(&d_absmax, EBSD_N_CONV * sizeof(float)));
-    for (int i = 1; i < EBSD_N_CONV; ++i) {
+    for (int i = 0; i < EBSD_N_CONV; ++i) {
         absmax_kernel<<<1, 1024, 0, st>>>(w->conv_w[i], 9 * kPlan[i].cin * kPlan[i].cout, d_absmax + i);
         EBSD_LAUNCH_CHECK();
     }
     float absmax[EBSD_N_CONV] = {};
-    EBSD_CUDA_TRY(cudaMemcpyAsync(absmax + 1, d_absmax + 1, (EBSD_N_CONV - 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    EBSD_CUDA_TRY(cudaMemcpyAsync(absmax, d_absmax, EBSD_N_CONV * sizeof(float), cudaMemcpyDeviceToHost, st));
     EBSD_CUDA_TRY(cudaStreamSynchronize(st));
     EBSD_CUDA_TRY(cudaFree(d_absmax));
     for (int i = 1; i < EBSD_N_CONV; ++i) {
@@ -349,6 +408,18 @@ int ebsd_encoder_create(ebsd_encoder **out, const ebsd_weights *w, int device, v
         EBSD_LAUNCH_CHECK();
         if ((rc = make_weight_map(&enc->w_map[i], enc->w_fused[i], cin, cout, kc, fused_weight_box_rows(i)))) return rc;
     }
+    {
+        // front end: conv0 weights times s0 / 255 (the pixel k stands for k / 255) with s0 the power of two that brings the
+        // largest of them into (64, 128], so that the fp16 hi AND lo halves sit in fp16's normal range
+        float s0 = 1.0f;
+        if (absmax[0] > 0.f && std::isfinite(absmax[0])) s0 = exp2f(floorf(log2f(128.0f * 255.0f / absmax[0])));
+        enc->c0_inv_scale = 1.0f / s0;
+        const float s1 = 1.0f / (kResidualScale * enc->corr_scale[1]);
+        EBSD_CUDA_TRY(cudaMalloc(&enc->w_front, FrontCfg::W_BYTES));
+        pack_front_weights_kernel<<<(FrontCfg::W_BYTES / 2 + 255) / 256, 256, 0, st>>>(w->conv_w[0], w->conv_w[1], s0, s1,
+                                                                                    enc->w_front);
+        EBSD_LAUNCH_CHECK();
+    }
     EBSD_CUDA_TRY(cudaMalloc(&enc->wh, 32 * 2048 * sizeof(float)));
     EBSD_CUDA_TRY(cudaMalloc(&enc->bh, 32 * sizeof(float)));
     pack_head_weights_kernel<<<(32 * 2048 + 255) / 256, 256, 0, st>>>(w->mu_w, w->logvar_w, w->mu_b, w->logvar_b,
@@ -362,6 +433,7 @@ int ebsd_encoder_create(ebsd_encoder **out, const ebsd_weights *w, int device, v
 void ebsd_encoder_destroy(ebsd_encoder *enc) {
     if (!enc) return;
     cudaFree(enc->w0);
+    cudaFree(enc->w_front);
     for (int i = 1; i < EBSD_N_CONV; ++i) cudaFree(enc->w_fused[i]);
     cudaFree(enc->wh);
     cudaFree(enc->bh);
@@ -404,6 +476,12 @@ int ebsd_encoder_forward(ebsd_encoder *enc, const void *patterns, int dtype, int
 
 #ifdef EBSD_ROLE_PROFILE
 void ebsd_profile_set_flags(int flags) { g_profile_flags = flags; }
+#endif
+#ifdef EBSD_DEBUG_NOTRAP
+// debugging build only: [0] = 1 if a bounded wait timed out, [1] = block << 32 | thread, [2] = barrier address, [3] = parity
+int ebsd_debug_timeout_info(unsigned long long *out4) {
+    return cudaMemcpyFromSymbol(out4, ebsd::g_timeout_info, 4 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -2;
+}
 #endif
 
 int ebsd_encoder_block(ebsd_encoder *enc, int layer, int dtype, const void *src, double *src_sums, int src_plane,

@@ -73,15 +73,34 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 #ifndef EBSD_WAIT_HINT_NS
 #define EBSD_WAIT_HINT_NS 20000u
 #endif
+#ifdef EBSD_DEBUG_NOTRAP
+// debugging build (tools/): a timed-out wait records (block, thread, barrier address, parity) and RETURNS, so that the
+// kernel drains and the host can read which wait starved (ebsd_debug_timeout_info)
+__device__ unsigned long long g_timeout_info[4];
+#define EBSD_TIMEOUT_ACTION(bar_u32, parity)                                                                        \
+    do {                                                                                                            \
+        if (atomicCAS(&g_timeout_info[0], 0ull, 1ull) == 0ull) {                                                     \
+            g_timeout_info[1] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;                                \
+            g_timeout_info[2] = (unsigned long long)(bar_u32);                                                       \
+            g_timeout_info[3] = (unsigned long long)(parity);                                                        \
+        }                                                                                                           \
+        return;                                                                                                     \
+    } while (0)
+#define EBSD_TIMEOUT_CYCLES 400000000ll
+#else
+#define EBSD_TIMEOUT_ACTION(bar_u32, parity)                                                              \
+    do {                                                                                                  \
+        printf("ebsd: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);                 \
+        __trap();                                                                                         \
+    } while (0)
+#define EBSD_TIMEOUT_CYCLES 4000000000ll   // ~2 s
+#endif
 // Bounded mbarrier wait: a mis-programmed pipeline must trap, not hang the GPU.
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait_hint(bar, parity, EBSD_WAIT_HINT_NS)) {
-        if (clock64() - t0 > 4000000000ll) {  // ~2 s
-            printf("ebsd encoder: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
+        if (clock64() - t0 > EBSD_TIMEOUT_CYCLES) EBSD_TIMEOUT_ACTION(smem_u32(bar), parity);
     }
 }
 

@@ -14,19 +14,26 @@
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ uint64_t desc(uint32_t saddr, int rowb) {
-    const uint64_t layout = rowb == 128 ? 2ull : 4ull;
+    const uint64_t layout = rowb == 128 ? 2ull : (rowb == 64 ? 4ull : 6ull);   // SWIZZLE_128B / 64B / 32B
     const uint64_t sbo = (8ull * rowb) >> 4;
     return (uint64_t)((saddr & 0x3ffffu) >> 4) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 __device__ __forceinline__ uint32_t idesc(int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+// KIND 1: kind::f8f6f4 (e4m3, K = 32 per instruction) instead of kind::f16
+template <int KIND>
 __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
-    asm volatile("{.reg .pred p; setp.eq.b32 p, 0, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;}"
-                 ::"r"(d), "l"(a), "l"(b), "r"(id) : "memory");
+    if (KIND)
+        asm volatile("{.reg .pred p; setp.eq.b32 p, 0, 0; tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;}"
+                     ::"r"(d), "l"(a), "l"(b), "r"(id) : "memory");
+    else
+        asm volatile("{.reg .pred p; setp.eq.b32 p, 0, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;}"
+                     ::"r"(d), "l"(a), "l"(b), "r"(id) : "memory");
 }
 
 // mode 0: all MMAs use N1.  mode 1: runs of `group` MMAs with N1 then `group` MMAs with N2 (different TMEM columns).
+template <int KIND>
 __global__ void __launch_bounds__(128, 1) rate(int n1, int n2, int group, int reps, int rowb, int shift_rows,
                                                long long *out) {
     extern __shared__ uint8_t raw[];
@@ -53,25 +60,27 @@ __global__ void __launch_bounds__(128, 1) rate(int n1, int n2, int group, int re
         const uint32_t id1 = idesc(n1), id2 = idesc(n2);
         const uint64_t da = desc(a0 + shift_rows * rowb, rowb), db = desc(b0, rowb);
         const uint64_t da2 = desc(a0 + 16384 + shift_rows * rowb, rowb);
+        const int kstep = rowb >= 128 ? 2 : (rowb == 64 ? ((0 + 1) & 1) * 2 : 0);   // 32-byte K steps inside a row (0: re-read)
         const long long t0 = clock64();
         if (group >= 8) {
             for (int r = 0; r < reps; ++r) {
                 for (int g = 0; g < group; g += 8) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) mma(tmem, da + (u & 3) * 2 + (u >> 2) * 64, db + (u & 3) * 2, id1, 1u);
+                    for (int u = 0; u < 8; ++u)
+                        mma<KIND>(tmem, da + (u & 3) * kstep + (u >> 2) * 64, db + (u & 3) * kstep, id1, 1u);
                 }
                 if (n2 > 0)
                     for (int g = 0; g < group; g += 8) {
 #pragma unroll
                         for (int u = 0; u < 8; ++u)
-                            mma(tmem + 256, da2 + (u & 3) * 2 + (u >> 2) * 64, db + (u & 3) * 2, id2, 1u);
+                            mma<KIND>(tmem + 256, da2 + (u & 3) * kstep + (u >> 2) * 64, db + (u & 3) * kstep, id2, 1u);
                     }
             }
         } else {
             for (int r = 0; r < reps; ++r) {
-                for (int g = 0; g < group; ++g) mma(tmem, da + g * 2, db + g * 2, id1, 1u);
+                for (int g = 0; g < group; ++g) mma<KIND>(tmem, da + g * 2, db + g * 2, id1, 1u);
                 if (n2 > 0)
-                    for (int g = 0; g < group; ++g) mma(tmem + 256, da2 + g * 2, db + g * 2, id2, 1u);
+                    for (int g = 0; g < group; ++g) mma<KIND>(tmem + 256, da2 + g * 2, db + g * 2, id2, 1u);
             }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&mbar)) : "memory");
@@ -88,22 +97,29 @@ __global__ void __launch_bounds__(128, 1) rate(int n1, int n2, int group, int re
 int main() {
     long long *d, h;
     CK(cudaMalloc(&d, 8));
-    CK(cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(rate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(rate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    int kind = 0;
     auto run = [&](int n1, int n2, int group, int rowb, int shift) {
         const int reps = 4096 / group;
-        rate<<<148, 128, 100 * 1024>>>(n1, n2, group, reps, rowb, shift, d);
-        CK(cudaDeviceSynchronize());
-        rate<<<148, 128, 100 * 1024>>>(n1, n2, group, reps, rowb, shift, d);
-        CK(cudaDeviceSynchronize());
+        for (int it = 0; it < 2; ++it) {
+            if (kind) rate<1><<<148, 128, 100 * 1024>>>(n1, n2, group, reps, rowb, shift, d);
+            else rate<0><<<148, 128, 100 * 1024>>>(n1, n2, group, reps, rowb, shift, d);
+            CK(cudaDeviceSynchronize());
+        }
         CK(cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost));
         const int total = reps * group * (n2 > 0 ? 2 : 1);
         const double ideal = reps * group * (n1 / 2.0 + (n2 > 0 ? n2 / 2.0 : 0.0));
         printf("rowb=%3d shift=%2d N1=%3d N2=%3d group=%4d : %9lld cycles, %7.1f per MMA, floor %7.1f -> %5.1f %% of floor rate\n",
                rowb, shift, n1, n2, group, h, (double)h / total, ideal / total, 100.0 * ideal / (double)h);
     };
-    for (int rowb : {128, 64})
-        for (int shift : {0, 1})
-            for (int n : {16, 32, 64, 96, 128, 192, 256}) run(n, 0, 64, rowb, shift);
+    for (kind = 0; kind < 2; ++kind) {
+        printf("---- %s\n", kind ? "kind::f8f6f4 (K = 32)" : "kind::f16 (K = 16)");
+        for (int rowb : {128, 64, 32})
+            for (int n : {16, 32, 64, 96, 128, 256}) run(n, 0, 64, rowb, 1);
+        // the front-end block's mix: fp16 N = 64 twice + (second kind set by g_kind_f8 only: run separately)
+    }
+    kind = 0;
     for (int group : {1, 2, 4, 8, 16, 32, 72})
         for (auto pr : {std::pair<int, int>{64, 32}, {128, 64}, {256, 128}}) run(pr.first, pr.second, group, 128, 1);
     for (int group : {1, 4, 16}) for (int n : {64, 128, 256}) run(n, n, group, 128, 1);
