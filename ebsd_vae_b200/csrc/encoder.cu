@@ -279,8 +279,8 @@ int launch_front(const ebsd_encoder *enc, const void *pats, const double *sums0,
     p.corr_scale = enc->corr_scale[1];
     p.nimg = nimg;
     p.nitems = nimg * C::ITEMS_PER_IMAGE;
-#ifdef EBSD_DEBUG_NOTRAP
-    p.dbg = getenv("EBSD_FRONT_DBG") ? atoi(getenv("EBSD_FRONT_DBG")) : 0;
+#if defined(EBSD_DEBUG_NOTRAP) || defined(EBSD_ROLE_PROFILE)
+    p.dbg = getenv("EBSD_FRONT_DBG") ? atoi(getenv("EBSD_FRONT_DBG")) : g_profile_flags;
 #endif
     const int sms = sm_count();
     const int per = (p.nitems + sms - 1) / sms;

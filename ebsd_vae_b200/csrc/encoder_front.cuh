@@ -78,11 +78,11 @@ struct FrontParams {
     float c0_inv_scale;       // 1 / s0: conv0's TMEM values are s0 x the true ones
     float corr_scale;         // 1 / (4096 s) of conv1's correction columns
     int nimg, nitems;
-#ifdef EBSD_DEBUG_NOTRAP
-    int dbg;                  // bisecting switches of the debugging build (tools/debug_front.py)
+#if defined(EBSD_DEBUG_NOTRAP) || defined(EBSD_ROLE_PROFILE)
+    int dbg;                  // role switches of the debugging / role-profiling builds (tools/debug_front.py, time_front.py)
 #endif
 };
-#ifdef EBSD_DEBUG_NOTRAP
+#if defined(EBSD_DEBUG_NOTRAP) || defined(EBSD_ROLE_PROFILE)
 #define FRONT_DBG(p, bit) (((p).dbg & (bit)) != 0)
 #else
 #define FRONT_DBG(p, bit) false

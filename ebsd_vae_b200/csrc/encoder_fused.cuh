@@ -361,10 +361,15 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    // PAIR: signals towards the leader's MMA issuer are collected LOCALLY in each CTA (one CTA-scope arrival per producer
+    // / epilogue warp) and the follower forwards each completed phase with ONE cluster-scope arrival from its otherwise
+    // idle warp 1 (the "relay").  A release.cluster arrival compiles to MEMBAR.ALL.GPU + ERRBAR: issued by every producer
+    // warp it waited for the global loads the warp had just put in flight for the next batch (ncu: 12 % membar + 12 % mio
+    // stalls in the 64 -> 64 block).
+    const uint32_t cta_rank = C::PAIR ? cluster_ctarank() : 0u;
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::A_STAGES; ++s) {
-            // PAIR: one arrival per producer warp of BOTH CTAs, collected on the leader's barrier
-            mbar_init(&a_full[s], C::PAIR ? 2 * (C::PRODUCERS / 32) : C::PRODUCERS);
+            mbar_init(&a_full[s], C::PAIR ? C::PRODUCERS / 32 + (cta_rank == 0 ? 1 : 0) : C::PRODUCERS);
             mbar_init(&a_empty[s], 1);
         }
         for (int s = 0; s < C::B_STAGES; ++s) {
@@ -373,7 +378,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull_bar[b], 1);
-            mbar_init(&tempty_bar[b], C::PAIR ? 8 : 4);  // PAIR: the epilogue warps of both CTAs release the leader
+            mbar_init(&tempty_bar[b], (C::PAIR && cta_rank == 0) ? 5 : 4);  // PAIR leader: own epilogue warps + the relay
             if (C::FIRST) {
                 mbar_init(&patch_full[b], 1);
                 mbar_init(&patch_empty[b], C::PRODUCERS / 32);
@@ -395,7 +400,6 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     if (C::PAIR) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t cta_rank = C::PAIR ? cluster_ctarank() : 0u;
 
     // contiguous item range per CTA: consecutive items belong to the same image, so plane statistics are
     // flushed once per image per warp instead of once per tile
@@ -495,6 +499,9 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 if (C::PAIR) mbar_wait_cluster(bar, parity);
                 else mbar_wait_bounded(bar, parity);
             };
+            // weight barriers complete by TMA transaction bytes only (both CTAs' loads are credited to the leader): no
+            // cluster-scope acquire, which costs an L1 invalidation (CCTL.IVALL) per wait
+            auto wait_tx = [&](uint64_t *bar, uint32_t parity) { mbar_wait_bounded(bar, parity); };
             // all MMAs of one plane for one tap: NT tiles x KSTEPS
             auto tap_mmas = [&](bool f8, uint32_t d_item, uint32_t win, uint32_t b_w, bool first) {
 #pragma unroll
@@ -505,7 +512,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                             umma_smem_desc_g<C::ROWB, 8>(b_w + k * 32), (first && k == 0) ? 0u : 1u);
             };
             if (C::RESIDENT_B) {
-                for (int kb = 0; kb < 9 * C::NCHUNK; ++kb) wait(&b_full[kb], 0);
+                for (int kb = 0; kb < 9 * C::NCHUNK; ++kb) wait_tx(&b_full[kb], 0);
                 tc_fence_after();
             }
             unsigned ait = 0, bit = 0;
@@ -543,7 +550,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                             const int dy = tap / 3, dx = tap - dy * 3;
                             const uint32_t shift = (uint32_t)((dy * C::PITCH + dx) * C::ROWB);
                             const int sb = bit % C::B_STAGES;
-                            wait(&b_full[sb], (bit / C::B_STAGES) & 1u);
+                            wait_tx(&b_full[sb], (bit / C::B_STAGES) & 1u);
                             tc_fence_after();
                             const uint32_t b_w = smem_u32(smem_b + sb * C::B_CTA);
                             tap_mmas(false, d_item, win_hi + shift, b_w, (cc | tap) == 0);
@@ -554,6 +561,23 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     commit(&a_empty[sa]);
                 }
                 commit(&tfull_bar[buf]);
+            }
+        }
+        if (C::PAIR && cta_rank != 0 && elect_one_sync()) {
+            // ===================== relay (follower CTA): forward locally completed phases to the leader's barriers
+            const unsigned total_a = (unsigned)(item_end - item_begin) * C::NCHUNK, total_t = (unsigned)(item_end - item_begin);
+            unsigned na = 0, nt = 0;
+            const long long t0 = clock64();
+            while (na < total_a || nt < total_t) {
+                if (na < total_a && mbar_try_wait_hint(&a_full[na % C::A_STAGES], (na / C::A_STAGES) & 1u, 200u)) {
+                    mbar_arrive_cluster(map_to_cta(smem_u32(&a_full[na % C::A_STAGES]), 0));
+                    ++na;
+                }
+                if (nt < total_t && mbar_try_wait(&tempty_bar[nt & 1], (nt >> 1) & 1u)) {
+                    mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[nt & 1]), 0));
+                    ++nt;
+                }
+                if (clock64() - t0 > EBSD_TIMEOUT_CYCLES) EBSD_TIMEOUT_ACTION(smem_u32(&a_full[0]), na);
             }
         }
     } else if (warp == 3 && C::FIRST) {
@@ -842,10 +866,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                if (C::PAIR) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[buf]), 0));
-                else mbar_arrive(&tempty_bar[buf]);
-            }
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);   // PAIR: the follower's relay forwards the completed phase
         }
         flush();
         if (lane == 0) bulk_wait_all();  // the staging buffers must outlive the TMA reads; stores complete before exit
@@ -946,7 +967,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 fence_proxy_async();
                 if (C::PAIR) {
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&a_full[sa]), 0));
+                    if (lane == 0) mbar_arrive(&a_full[sa]);
                 } else {
                     mbar_arrive(&a_full[sa]);
                 }
@@ -1047,7 +1068,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     fence_proxy_async();
                     if (C::PAIR) {
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&a_full[ait % C::A_STAGES]), 0));
+                        if (lane == 0) mbar_arrive(&a_full[ait % C::A_STAGES]);
                     } else {
                         mbar_arrive(&a_full[ait % C::A_STAGES]);
                     }

@@ -94,11 +94,72 @@ __global__ void __launch_bounds__(128, 1) rate(int n1, int n2, int group, int re
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
-int main() {
+// runs of `group` kind::f16 MMAs (N = n1) alternating with runs of `group` kind::f8f6f4 MMAs (N = n2): the cost of a
+// KIND switch in the issue stream (the encoder blocks issue both kinds into one accumulator pair)
+__global__ void __launch_bounds__(128, 1) rate_kinds(int n1, int n2, int group, int reps, long long *out) {
+    extern __shared__ uint8_t raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tslot;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) ((uint32_t *)smem)[i] = 0u;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s32(&tslot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tslot;
+    if (threadIdx.x == 0) {
+        const uint32_t a0 = s32(smem), b0 = s32(smem) + 48 * 1024;
+        const uint32_t id1 = idesc(n1), id2 = idesc(n2);
+        const uint64_t da = desc(a0 + 128, 128), db = desc(b0, 128), da2 = desc(a0 + 16384 + 128, 128);
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            for (int g = 0; g < group; ++g) mma<0>(tmem, da + (g & 3) * 2, db + (g & 3) * 2, id1, 1u);
+            for (int g = 0; g < group; ++g) mma<1>(tmem + 256, da2 + (g & 3) * 2, db + (g & 3) * 2, id2, 1u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&mbar)) : "memory");
+        uint32_t ok = 0;
+        while (!ok) asm volatile("{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0,1,0,p;}" : "=r"(ok) : "r"(s32(&mbar)));
+        const long long t1 = clock64();
+        if (blockIdx.x == 0) out[0] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+int main(int argc, char **argv) {
     long long *d, h;
     CK(cudaMalloc(&d, 8));
     CK(cudaFuncSetAttribute(rate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CK(cudaFuncSetAttribute(rate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(rate_kinds, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    if (argc > 1 && argv[1][0] == 'k') {
+        // kind alternation only: ./mma_rate k
+        for (auto pr : {std::pair<int, int>{128, 128}, {64, 64}, {64, 32}, {256, 256}})
+            for (int group : {1, 2, 4, 8, 12, 16, 36, 72}) {
+                const int reps = 2304 / group;
+                for (int it = 0; it < 2; ++it) {
+                    rate_kinds<<<148, 128, 100 * 1024>>>(pr.first, pr.second, group, reps, d);
+                    CK(cudaDeviceSynchronize());
+                }
+                CK(cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost));
+                const double per = (double)h / (2.0 * reps * group);
+                const double floor_ = (pr.first / 2.0 > 46 ? pr.first / 2.0 : 46.0) * 0.5 + (pr.second / 2.0 > 46 ? pr.second / 2.0 : 46.0) * 0.5;
+                printf("f16 N=%3d x %d  <->  f8 N=%3d x %d : %7.1f cycles per MMA (unswitched ~%5.1f) -> %6.1f cycles per switch\n",
+                       pr.first, group, pr.second, group, per, floor_, (per - floor_) * group);
+            }
+        cudaFree(d);
+        return 0;
+    }
     int kind = 0;
     auto run = [&](int n1, int n2, int group, int rowb, int shift) {
         const int reps = 4096 / group;

@@ -20,9 +20,12 @@ import re
 import subprocess
 import sys
 
-TENSOR = ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
-          "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
-          "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed")
+# Calibration (profiles/r02_tensor_metric_calibration.txt: tools/mma_rate.cu under `ncu --set full`): a back-to-back
+# M128 x N256 x K16 stream reads 96 % on sm__pipe_tensor_cycles_active (kind::f16 AND kind::f8f6f4), while the
+# `_realtime` variant reads 8 / 33 / 13 / 21 % for launches of that same full-rate kernel -- it is not usable.
+TENSOR = ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+          "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed",
+          "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed")
 WANT = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "sm__cycles_elapsed.avg.per_second", "smsp__issue_active.avg.pct_of_peak_sustained_active") + TENSOR
@@ -76,7 +79,7 @@ def main():
              f"tensor metric: {tensor_metric}",
              f"{'kernel':58s} {'us':>9s} {'DRAM rd MB':>11s} {'DRAM wr MB':>11s} {'tensor %':>9s} {'mem-tensor %':>12s} {'L2 hit %':>9s} {'SM MHz':>7s}"]
     for name, us, rd, wr, tp, mt, l2, mhz in table:
-        lines.append(f"{name[:58]:58s} {us:9.1f} {rd / 1e6:11.1f} {wr / 1e6:11.1f} {tp:9.1f} {mt:12.1f} {l2:9.1f} {mhz / 1e6 if mhz > 1e5 else mhz:7.0f}")
+        lines.append(f"{name[:58]:58s} {us:9.1f} {rd / 1e6:11.1f} {wr / 1e6:11.1f} {tp:9.1f} {mt:12.1f} {l2:9.1f} {mhz / 1e6 if mhz > 1e5 else (mhz * 1e3 if mhz < 10 else mhz):7.0f}")
     tw = tensor_weighted / tot_us if tot_us else float("nan")
     lines.append(f"{'chain total':58s} {tot_us:9.1f} {'':11s} {tot_bytes / 1e6:11.1f} {tw:9.1f}   (tensor % weighted by kernel time)")
     lines.append(f"DRAM bytes per pattern: {tot_bytes / n_patterns:,.0f}   (algorithmic: 16 384 in + 128 out)")
