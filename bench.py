@@ -495,8 +495,8 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
     peak_tf = peaks["bf16_tflops_sustained"]  # the encoder runs for tens of ms per step: sustained figure
     ncu = load_ncu_chain()
     roofline = {
-        "kernel": "ebsd_encoder_forward: conv/InstanceNorm/pool chain + heads (dominant, %.1f %% of the step)"
-                  % (100.0 * enc_ms / ms_step),
+        "kernel": "ebsd_encoder_forward: conv/InstanceNorm/pool chain + heads (dominant, %.1f %% of the summed stage times)"
+                  % (100.0 * enc_ms / max(enc_ms + stages.get("search_global_ms", stages["topk_ms"]) + stages["consensus_ms"], 1e-9)),
         "bound": "tensor", "achieved": enc_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": enc_tflops / peak_tf,
         "traffic": (N_QUERY_PER_GPU * ncu["dram_bytes_per_pattern"]) if ncu else None,
         "traffic_note": ("DRAM bytes per step of the encoder chain = dram__bytes_read.sum + dram__bytes_write.sum over the "

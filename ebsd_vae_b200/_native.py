@@ -44,6 +44,7 @@ SYMBOLS = {
     "ebsd_launch_count": (ctypes.c_uint64, []),
     "ebsd_quantize_crop": (_int, [_c_void_p, _int, _i64, _int, _int, _int, _int, _int, _int, _int, _int, _c_void_p,
                                   _c_void_p]),
+    "ebsd_parse_angle_text": (_i64, [ctypes.c_char_p, _size_t, _c_void_p, _i64]),
     "ebsd_encoder_create": (_int, [ctypes.POINTER(_c_void_p), ctypes.POINTER(EbsdWeights), _int, _c_void_p]),
     "ebsd_encoder_destroy": (None, [_c_void_p]),
     "ebsd_encoder_workspace_bytes": (_size_t, [_c_void_p, _i64]),

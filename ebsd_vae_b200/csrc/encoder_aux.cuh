@@ -186,4 +186,21 @@ __global__ void __launch_bounds__(256) conv0_stats_kernel(const void *__restrict
     }
 }
 
+// Running sum of fp32 partial sums as an unevaluated (hi, lo) pair (Knuth's TwoSum: hi + lo carries the sum to ~2^-48
+// relative, whatever the order the partials arrive in), converted to fp64 only when it is flushed to memory.  The plane
+// statistics used to be accumulated as `double += (double)partial`: F2F.F64.F32 + DADD per (tile, channel block) cost the
+// epilogue warps 5-7 % of a whole block (ncu: math-pipe throttle on exactly those lines; role profile flag 32).
+struct PairSum {
+    float hi, lo;
+    __device__ __forceinline__ void clear() { hi = lo = 0.f; }
+    __device__ __forceinline__ void add(float x) {
+        const float s = __fadd_rn(hi, x);
+        const float bb = __fadd_rn(s, -hi);
+        const float e = __fadd_rn(__fadd_rn(hi, -__fadd_rn(s, -bb)), __fadd_rn(x, -bb));
+        hi = s;
+        lo = __fadd_rn(lo, e);
+    }
+    __device__ __forceinline__ double value() const { return (double)hi + (double)lo; }
+};
+
 }  // namespace ebsd

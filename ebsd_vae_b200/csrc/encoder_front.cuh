@@ -332,14 +332,15 @@ front_u8_kernel(const __grid_constant__ CUtensorMap map_pat, const __grid_consta
         const int a_par = xl & 1, b_par = g & 1;
         const int prow = (lane >> 4) * 4 + (xl >> 1);   // pooled pixel of this lane in the warp's [2 y][4 x] box
         const uint32_t stg_u32 = smem_u + C::OFF_STG + (uint32_t)((hf * 4 + quarter) * C::WSTG);   // [tile][8 px x 64 B]
-        // running plane sums in fp64 (see encoder_fused.cuh): lane c < 16 holds the sum of channel hf*16 + c, lane
+        // running plane sums as (hi, lo) fp32 pairs (PairSum, encoder_aux.cuh): lane c < 16 holds the sum of channel hf*16 + c, lane
         // 16 + c its sum of squares
-        double accum = 0.0;
+        PairSum accum;
+        accum.clear();
         int cur_n = -1;
         auto flush = [&]() {
             if (cur_n >= 0 && cur_n < p.nimg)
-                atomicAdd(p.sums + ((long long)cur_n * COUT + hf * 16 + (lane & 15)) * 2 + (lane >> 4), accum);
-            accum = 0.0;
+                atomicAdd(p.sums + ((long long)cur_n * COUT + hf * 16 + (lane & 15)) * 2 + (lane >> 4), accum.value());
+            accum.clear();
         };
         for (int j = 0; j < n_items; ++j) {
             const int buf = j & 1;
@@ -399,7 +400,7 @@ front_u8_kernel(const __grid_constant__ CUtensorMap map_pat, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);   // the accumulator is free before the (shuffle-heavy) reduction
-            if (!FRONT_DBG(p, 64)) accum += (double)warp_transpose_reduce32(z, lane);
+            if (!FRONT_DBG(p, 64)) accum.add(warp_transpose_reduce32(z, lane));
         }
         flush();
         if (lane == 0) bulk_wait_all();  // the staging buffers must outlive the TMA reads; stores complete before exit

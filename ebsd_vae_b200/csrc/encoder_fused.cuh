@@ -155,7 +155,8 @@ struct FusedParams {
     int nitems;
 #ifdef EBSD_ROLE_PROFILE
     int dbg;                 // role-profiling build only (tools/time_fused.py): 1 producers write nothing, 2 no MMAs,
-                             // 4 epilogue does nothing but release TMEM, 8 no plane statistics, 16 no stores
+                             // 4 epilogue does nothing but release TMEM, 8 no plane statistics, 16 no stores,
+                             // 32 statistics without the fp64 accumulation (W >= 16 blocks with register sums)
 #endif
 };
 #ifdef EBSD_ROLE_PROFILE
@@ -646,21 +647,27 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         // (TILE_FLUSH; 4-8x more fp64 reductions at the L2, still a few hundred per image).
         constexpr bool TILE_FLUSH = NCB >= 4;
         constexpr int NACC = TILE_FLUSH ? 1 : NCB;
-        double acc1[NACC][C::NI], acc2[NACC][C::NI];
+        PairSum acc1[NACC][C::NI], acc2[NACC][C::NI];   // (hi, lo) fp32 pairs, fp64 only at the flush (encoder_aux.cuh)
 #pragma unroll
         for (int cb = 0; cb < NACC; ++cb)
 #pragma unroll
-            for (int s = 0; s < C::NI; ++s) acc1[cb][s] = acc2[cb][s] = 0.0;
-        double accum_lo = 0.0, accum_hi = 0.0;  // ACCUM: lane c < 16: sum of channel c (lo) / 16 + c (hi); lanes >= 16: squares
+            for (int s = 0; s < C::NI; ++s) {
+                acc1[cb][s].clear();
+                acc2[cb][s].clear();
+            }
+        PairSum accum_lo, accum_hi;  // ACCUM: lane c < 16: sum of channel c (lo) / 16 + c (hi); lanes >= 16: squares
+        accum_lo.clear();
+        accum_hi.clear();
         int cur_n = -1;
         auto flush = [&]() {
             if (C::ACCUM) {
                 if (cur_n >= 0 && cur_n < p.nimg) {
                     double *dst = p.sums + ((long long)cur_n * COUT + (lane & 15)) * 2 + (lane >> 4);
-                    atomicAdd(dst, accum_lo);
-                    atomicAdd(dst + 32, accum_hi);
+                    atomicAdd(dst, accum_lo.value());
+                    atomicAdd(dst + 32, accum_hi.value());
                 }
-                accum_lo = accum_hi = 0.0;
+                accum_lo.clear();
+                accum_hi.clear();
                 return;
             }
             if (TILE_FLUSH) return;
@@ -671,8 +678,8 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 #pragma unroll
                         for (int cb = 0; cb < NACC; ++cb) {
                             double *dst = p.sums + ((long long)(cur_n + s) * COUT + cb * 32 + lane) * 2;
-                            atomicAdd(dst, acc1[cb][s]);
-                            atomicAdd(dst + 1, acc2[cb][s]);
+                            atomicAdd(dst, acc1[cb][s].value());
+                            atomicAdd(dst + 1, acc2[cb][s].value());
                         }
                     }
                 }
@@ -680,7 +687,10 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 #pragma unroll
             for (int cb = 0; cb < NACC; ++cb)
 #pragma unroll
-                for (int s = 0; s < C::NI; ++s) acc1[cb][s] = acc2[cb][s] = 0.0;
+                for (int s = 0; s < C::NI; ++s) {
+                    acc1[cb][s].clear();
+                    acc2[cb][s].clear();
+                }
         };
         int j = 0;
         for (int item = item_begin; item < item_end; ++item, ++j) {
@@ -759,8 +769,8 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                         // one 32-wide transposing reduction serves both quantities: lane c < 16 ends up with the sum
                         // of channel hf*16 + c, lane 16 + c with its sum of squares
                         const float red = warp_transpose_reduce32(z, lane);
-                        if (hf == 0) accum_lo += (double)red;
-                        else accum_hi += (double)red;
+                        if (hf == 0) accum_lo.add(red);
+                        else accum_hi.add(red);
                     }
                 }
             } else {
@@ -835,9 +845,11 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                                 atomicAdd(dst, (double)t1);
                                 atomicAdd(dst + 1, (double)t2);
                             }
+                        } else if (EBSD_DBG(p) & 32) {   // role profiling: the reductions without the fp64 accumulation
+                            if (t1 + t2 == 12345.678f) acc1[0][0].add(1.0f);
                         } else {
-                            acc1[TILE_FLUSH ? 0 : cb][0] += (double)t1;
-                            acc2[TILE_FLUSH ? 0 : cb][0] += (double)t2;
+                            acc1[TILE_FLUSH ? 0 : cb][0].add(t1);
+                            acc2[TILE_FLUSH ? 0 : cb][0].add(t2);
                         }
                     } else {
 #pragma unroll
@@ -856,8 +868,8 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                                     atomicAdd(dst + 1, (double)t2);
                                 }
                             } else {
-                                acc1[TILE_FLUSH ? 0 : cb][s] += (double)t1;
-                                acc2[TILE_FLUSH ? 0 : cb][s] += (double)t2;
+                                acc1[TILE_FLUSH ? 0 : cb][s].add(t1);
+                                acc2[TILE_FLUSH ? 0 : cb][s].add(t2);
                             }
                         }
                     }

@@ -540,7 +540,6 @@ __global__ void __launch_bounds__(256) topk_rerank_kernel(const float *__restric
 #pragma unroll
     for (int c = 0; c < 4; ++c) qv[c] = __ldg((const float4 *)(queries + q * kD) + c);
     const int qt = (int)(q / kScrM), m = (int)(q % kScrM);
-    const long long total_tiles = p.tile_end;
     float e_dot = -INFINITY;
     int e_idx = kIdxEmpty;
     if (init_from_out && lane < p.k) {   // a sorted list: lane l takes entry l
@@ -551,8 +550,17 @@ __global__ void __launch_bounds__(256) topk_rerank_kernel(const float *__restric
         }
     }
     __syncwarp();
-    for (int split = 0; split < p.n_splits; ++split) {
-        const int item = split * p.n_qtiles + qt;
+    // the items of this query tile: the CTAs whose unit spans intersect [qt T, (qt + 1) T) (ScreenParams)
+    const long long T = p.tile_end - p.tile_begin, u_lo = (long long)qt * T, u_hi = u_lo + T;
+    long long c = u_lo * p.n_ctas / ((long long)p.n_qtiles * T);
+    while (c > 0 && screen_span_begin(p, c) > u_lo) --c;
+    while (c + 1 < p.n_ctas && screen_span_begin(p, c + 1) <= u_lo) ++c;
+    for (; c < p.n_ctas; ++c) {
+        const long long s0 = screen_span_begin(p, c), s1 = screen_span_begin(p, c + 1);
+        if (s0 >= u_hi) break;
+        const long long lo = s0 > u_lo ? s0 : u_lo, hi = s1 < u_hi ? s1 : u_hi;
+        if (lo >= hi) continue;   // a CTA without units (fewer units than CTAs)
+        const int item = (int)c + qt;
         for (int half = 0; half < kScrGroups; ++half) {
             const long long slot = ((long long)item * kScrGroups + half) * kScrM + m;
             const int n = p.cand_n[slot];
@@ -570,9 +578,7 @@ __global__ void __launch_bounds__(256) topk_rerank_kernel(const float *__restric
                         warp_insert<int>(e_dot, e_idx, __shfl_sync(0xffffffffu, d, j2), __shfl_sync(0xffffffffu, row, j2), lane);
                 }
             } else {
-                const long long tile0 = p.tile_begin + (long long)split * p.tiles_per_split;
-                long long tile1 = tile0 + p.tiles_per_split;
-                if (tile1 > total_tiles) tile1 = total_tiles;
+                const long long tile0 = p.tile_begin + (lo - u_lo), tile1 = p.tile_begin + (hi - u_lo);
                 for (long long t = tile0; t < tile1; ++t)
                     for (int c0 = 0; c0 < kScrGroupCols; c0 += 32) {
                         const long long row = t * kScrN + half * kScrGroupCols + c0 + lane;
@@ -652,7 +658,7 @@ static TopkPlan make_plan(long long N, long long Q, int sms) {
 
 // ---- tensor-core screen (topk_screen.cuh): plan, workspace carving, launch
 struct ScreenPlan {
-    int n_qtiles, n_splits, tiles_per_split, items;
+    int n_qtiles, items;
     size_t off_dpairs, off_qpairs, off_cs, off_ci, off_cn, off_parts, bytes;
 };
 
@@ -665,6 +671,40 @@ static long long screen_prefix_rows(long long N) {
     long long n0 = N / 8;   // called with N = the rows of stage B (N/8 of the dictionary): n0 = N/64
     if (n0 < 4096) n0 = 4096;
     return n0 < N ? n0 : N;
+}
+
+// Stage boundaries of the screen in 256-row tiles, ascending: [0] = rows of the exact CUDA-core seeding search (not
+// tile aligned), then the END tile of every screen pass; each pass covers 8x the rows of the one before
+// (N/512, N/64, N/8, N -- as many levels as keep the seed at >= 4096 rows).  The CUDA-core search costs ~12 ns per
+// row and 10k queries against ~1 ns for the screen, so it should only ever see a few thousand rows: at 1.25 M x 80 k
+// (one shard of the 10 M-row dictionary on 8 GPUs) the N/64 seed alone was 2 of 16.8 ms.
+// EBSD_TOPK_SCREEN_LEVELS=n caps the number of screen passes (A/B timing; 2 = the round-1 staging).
+struct ScreenStages {
+    long long seed_rows;
+    int n_pass;
+    long long pass_end[8];   // tiles
+};
+static ScreenStages screen_stages(long long N) {
+    static int max_levels = -1;
+    if (max_levels < 0) {
+        const char *e = getenv("EBSD_TOPK_SCREEN_LEVELS");
+        max_levels = (e && atoi(e) >= 1 && atoi(e) <= 8) ? atoi(e) : 8;
+    }
+    const long long total_tiles = (N + kScrN - 1) / kScrN;
+    long long ends[8];
+    int n = 0;
+    ends[n++] = total_tiles;
+    long long rows = N;
+    while (n < max_levels && rows / 8 >= 8192) {
+        rows /= 8;
+        ends[n++] = (rows + kScrN - 1) / kScrN;
+    }
+    ScreenStages st;
+    st.seed_rows = screen_prefix_rows(ends[n - 1] * kScrN);
+    if (st.seed_rows > N) st.seed_rows = N;
+    st.n_pass = n;
+    for (int i = 0; i < n; ++i) st.pass_end[i] = ends[n - 1 - i];
+    return st;
 }
 
 constexpr long long kScreenQueryChunk = 131072;   // queries per screen pass (bounds the survivor buffers at ~256 MiB)
@@ -696,13 +736,8 @@ static ScreenPlan make_screen_plan(long long N, long long Q, int sms) {
     ScreenPlan pl;
     pl.n_qtiles = (int)((Q + kScrM - 1) / kScrM);
     const long long total_tiles = (N + kScrN - 1) / kScrN;
-    long long s = (2ll * sms + pl.n_qtiles - 1) / pl.n_qtiles;          // aim at two waves of work items
-    if (s > total_tiles / 8) s = total_tiles / 8;                         // at least 8 tiles per split
-    if (s > 1024 / pl.n_qtiles) s = 1024 / pl.n_qtiles;                   // bounds the candidate buffers (~256 KiB/item)
-    if (s < 1) s = 1;
-    pl.tiles_per_split = (int)((total_tiles + s - 1) / s);
-    pl.n_splits = (int)((total_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split);
-    pl.items = pl.n_qtiles * pl.n_splits;
+    (void)total_tiles;
+    pl.items = sms + pl.n_qtiles;   // balanced unit spans: item ids are cta + query tile (ScreenParams)
     size_t off = 0;
     auto take = [&](size_t bytes) {
         const size_t r = off;
@@ -715,9 +750,8 @@ static ScreenPlan make_screen_plan(long long N, long long Q, int sms) {
     pl.off_cs = take(slots * kScrCap * sizeof(float));
     pl.off_ci = take(slots * kScrCap * sizeof(int));
     pl.off_cn = take(slots * sizeof(int));
-    // partial lists of the stage-A seeding search (the CUDA-core kernel over N/64 rows, see run_screen)
-    const long long n1_rows = ((N / 8 + kScrN - 1) / kScrN) * kScrN;
-    const TopkPlan ex = make_plan(screen_prefix_rows(n1_rows), Q, sms);
+    // partial lists of the seeding search (the CUDA-core kernel over the first few thousand rows, see run_screen)
+    const TopkPlan ex = make_plan(screen_stages(N).seed_rows, Q, sms);
     pl.off_parts = take(ex.n_splits > 1 ? (size_t)ex.n_splits * (size_t)Q * 32 * sizeof(Entry) : 1024);
     pl.bytes = off + 1024;
     return pl;
@@ -899,9 +933,9 @@ static int run_screen(const float *dict, long long N, long long index_base, cons
     if ((rc = make_pairs_map(&map_d, dpairs, drows, kScrN))) return rc;
     if ((rc = make_pairs_map(&map_q, qpairs, qrows, kScrM))) return rc;
     // Thresholds are seeded in stages, each giving k rows whose exact dots bound the final k-th best from below:
-    //   A  CUDA-core search of the first n0 = N/64 rows                    -> exact top-k of [0, n0)
-    //   B  screen + re-rank of the first n1 = N/8 rows, thr from A         -> exact top-k of [0, n1)   (~8k survivors)
-    //   C  screen of the remaining rows [n1, N), thr from B; the re-rank starts from B's list -> top-k of [0, N)
+    //   seed    CUDA-core search of the first few thousand rows                  -> exact top-k of [0, n0)
+    //   pass 0  screen + re-rank of the first 8 n0 rows, thr from the seed        -> exact top-k of that prefix
+    //   pass i  screen of the next 8x rows, thr from pass i-1; the re-rank starts from its list (~8k survivors each)
     // out_dot / out_idx carry the running exact lists between the stages (each kernel reads them before the next
     // one overwrites them: same stream).
     static bool configured[kMaxDevices] = {};   // function attributes are per device
@@ -910,10 +944,9 @@ static int run_screen(const float *dict, long long N, long long index_base, cons
         EBSD_CUDA_TRY(cudaFuncSetAttribute(topk_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScrSmem));
         configured[dev] = true;
     }
-    const long long n1_tiles = ((N / 8 + kScrN - 1) / kScrN);
-    long long n0 = screen_prefix_rows(n1_tiles * kScrN);   // N/64, at least 4096
-    if (n0 > N) n0 = N;
-    if ((rc = run_exact(dict, n0, index_base, queries, Q, k, out_dot, out_idx, nullptr, ws + pl.off_parts, sms, st))) return rc;
+    const ScreenStages stages = screen_stages(N);
+    if ((rc = run_exact(dict, stages.seed_rows, index_base, queries, Q, k, out_dot, out_idx, nullptr, ws + pl.off_parts, sms, st)))
+        return rc;
     auto pass = [&](long long tile_begin, long long tile_end, int init_from_out) -> int {
         ScreenParams p;
         p.Q = Q;
@@ -922,19 +955,13 @@ static int run_screen(const float *dict, long long N, long long index_base, cons
         p.n_qtiles = pl.n_qtiles;
         p.tile_begin = tile_begin;
         p.tile_end = tile_end;
-        // split the pass over the same number of work items per query tile as the plan allows
-        long long s = pl.n_splits;
-        const long long tiles = tile_end - tile_begin;
-        if (s > tiles / 8) s = tiles / 8;
-        if (s < 1) s = 1;
-        p.tiles_per_split = (int)((tiles + s - 1) / s);
-        p.n_splits = (int)((tiles + p.tiles_per_split - 1) / p.tiles_per_split);
+        const long long units = (long long)p.n_qtiles * (tile_end - tile_begin);
+        const int grid = units < sms ? (int)(units < 1 ? 1 : units) : sms;
+        p.n_ctas = grid;
         p.tau0 = out_dot;
         p.cand_s = (float *)(ws + pl.off_cs);
         p.cand_i = (int *)(ws + pl.off_ci);
         p.cand_n = (int *)(ws + pl.off_cn);
-        const int items = p.n_qtiles * p.n_splits;
-        const int grid = items < sms ? items : sms;
         topk_screen_kernel<<<grid, kScrThreads, kScrSmem, st>>>(map_d, map_q, p);
         EBSD_LAUNCH_CHECK();
         const int wpb = 8;
@@ -943,8 +970,13 @@ static int run_screen(const float *dict, long long N, long long index_base, cons
         EBSD_LAUNCH_CHECK();
         return EBSD_OK;
     };
-    if ((rc = pass(0, n1_tiles, 0))) return rc;
-    return pass(n1_tiles, total_tiles, 1);
+    long long begin = 0;
+    for (int i = 0; i < stages.n_pass; ++i) {
+        if (stages.pass_end[i] <= begin) continue;
+        if ((rc = pass(begin, stages.pass_end[i], i > 0 ? 1 : 0))) return rc;
+        begin = stages.pass_end[i];
+    }
+    return EBSD_OK;
 }
 
 // Workspace of the screen path for Q queries: ebsd_topk runs it in chunks of kScreenQueryChunk queries and every

@@ -46,16 +46,46 @@ constexpr float kScrEps = 1e-5f;
 constexpr int kScrThreads = 128 + 128 * kScrGroups;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4.. epilogue (lane quarter x column group)
 constexpr int kScrSmem = 1024 + kScrStages * kScrTileB + kScrQB + 256;
 
+// Work distribution.  A pass covers the dictionary tiles [tile_begin, tile_end) for every query tile: U = n_qtiles * T
+// (query tile, dictionary tile) units, query-tile major.  CTA c of n_ctas takes the contiguous span
+// [c U / n_ctas, (c + 1) U / n_ctas) -- every CTA gets the same number of units to within one (with whole (query tile,
+// dictionary split) items dealt round-robin, 316 items on 148 CTAs left 29 % of the kernel idle at 10 M x 10 k) -- and
+// walks it as ITEMS = maximal pieces inside one query tile.  Along the chain of CTAs either the CTA or the query tile
+// advances from one item to the next, so `cta + qt` numbers the items uniquely (< n_ctas + n_qtiles): that is the
+// slot of the item's survivor buffers, which the re-rank finds again with the same arithmetic.
 struct ScreenParams {
     long long Q, N;
     int k;
-    int n_qtiles, n_splits, tiles_per_split;
+    int n_qtiles, n_ctas;
     long long tile_begin, tile_end;   // dictionary tiles (256 rows each) this pass covers
     const float *tau0;  // [Q][k]: exact top-k dots of a dictionary prefix (column k-1 seeds the threshold)
     float *cand_s;      // [items][groups][128][CAP] approximate dots
     int *cand_i;        // [items][groups][128][CAP] shard-local rows
     int *cand_n;        // [items][groups][128]      entries used
 };
+
+struct ScreenItem {
+    int qt, id;
+    long long tile0, tile1;   // absolute dictionary tiles
+};
+__host__ __device__ inline long long screen_span_begin(const ScreenParams &p, long long cta) {
+    const long long units = (long long)p.n_qtiles * (p.tile_end - p.tile_begin);
+    return cta * units / p.n_ctas;
+}
+// the item that starts at unit u of CTA `cta`'s span [.., u_end); advances u past it
+__device__ __forceinline__ ScreenItem screen_item_at(const ScreenParams &p, int cta, long long &u, long long u_end) {
+    const long long T = p.tile_end - p.tile_begin;
+    ScreenItem it;
+    it.qt = (int)(u / T);
+    const long long t0 = u - (long long)it.qt * T;
+    long long t1 = t0 + (u_end - u);
+    if (t1 > T) t1 = T;
+    it.id = cta + it.qt;
+    it.tile0 = p.tile_begin + t0;
+    it.tile1 = p.tile_begin + t1;
+    u += t1 - t0;
+    return it;
+}
 
 // fp32 rows [n,16] -> fp16 pairs [n][hi(16) | lo(16)]
 __global__ void split_rows_f16_kernel(const float *__restrict__ x, __half *__restrict__ out, long long n) {
@@ -155,22 +185,18 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const long long total_tiles = p.tile_end;
-    const int n_items = p.n_qtiles * p.n_splits;
+    const long long u_begin = screen_span_begin(p, blockIdx.x), u_end = screen_span_begin(p, (long long)blockIdx.x + 1);
 
     if (warp == 0) {
         // ===================== TMA: the query tile of an item once, then its dictionary tiles
         if (elect_one_sync()) {
             unsigned it = 0, qit = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++qit) {
-                const int split = item / p.n_qtiles, qt = item - split * p.n_qtiles;
-                const long long tile0 = p.tile_begin + (long long)split * p.tiles_per_split;
-                long long tile1 = tile0 + p.tiles_per_split;
-                if (tile1 > total_tiles) tile1 = total_tiles;
+            for (long long u = u_begin; u < u_end; ++qit) {
+                const ScreenItem item = screen_item_at(p, blockIdx.x, u, u_end);
                 mbar_wait_bounded(q_empty, (qit & 1u) ^ 1u);
                 mbar_expect_tx(q_full, kScrQB);
-                tma_load_2d(smem_q, &map_q, 0, qt * kScrM, q_full);
-                for (long long t = tile0; t < tile1; ++t, ++it) {
+                tma_load_2d(smem_q, &map_q, 0, item.qt * kScrM, q_full);
+                for (long long t = item.tile0; t < item.tile1; ++t, ++it) {
                     const int s = it % kScrStages;
                     mbar_wait_bounded(&d_empty[s], ((it / kScrStages) & 1u) ^ 1u);
                     mbar_expect_tx(&d_full[s], kScrTileB);
@@ -187,15 +213,12 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
             // accumulator per tile the hand-off was a latency chain: ~1400 cycles per tile against a 450-cycle drain).
             constexpr uint32_t idesc = umma_idesc_f16(kScrN / 2);
             unsigned it = 0, qit = 0, tj = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++qit) {
-                const int split = item / p.n_qtiles;
-                const long long tile0 = p.tile_begin + (long long)split * p.tiles_per_split;
-                long long tile1 = tile0 + p.tiles_per_split;
-                if (tile1 > total_tiles) tile1 = total_tiles;
+            for (long long u = u_begin; u < u_end; ++qit) {
+                const ScreenItem item = screen_item_at(p, blockIdx.x, u, u_end);
                 mbar_wait_bounded(q_full, qit & 1u);
                 tc_fence_after();
                 const uint32_t qa = smem_u32(smem_q);
-                for (long long t = tile0; t < tile1; ++t, ++it, ++tj) {
+                for (long long t = item.tile0; t < item.tile1; ++t, ++it, ++tj) {
                     const int s = it % kScrStages;
                     mbar_wait_bounded(&d_full[s], (it / kScrStages) & 1u);
 #pragma unroll
@@ -226,13 +249,12 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
         asm volatile("mov.u32 %0, %1;" : "=r"(tfull_u32) : "r"(smem_u32(tfull) + (uint32_t)((half >> 1) * 8)));
         asm volatile("mov.u32 %0, %1;" : "=r"(tempty_u32) : "r"(smem_u32(tempty) + (uint32_t)((half >> 1) * 8)));
         unsigned tj = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int split = item / p.n_qtiles, qt = item - split * p.n_qtiles;
-            const long long tile0 = p.tile_begin + (long long)split * p.tiles_per_split;
-            long long tile1 = tile0 + p.tiles_per_split;
-            if (tile1 > total_tiles) tile1 = total_tiles;
+        for (long long u = u_begin; u < u_end;) {
+            const ScreenItem item = screen_item_at(p, blockIdx.x, u, u_end);
+            const int qt = item.qt;
+            const long long tile0 = item.tile0, tile1 = item.tile1;
             const bool live = (long long)qt * kScrM + m < p.Q;
-            const long long slot = ((long long)item * kScrGroups + half) * kScrM + m;
+            const long long slot = ((long long)item.id * kScrGroups + half) * kScrM + m;
             float *cs = p.cand_s + slot * kScrCap;
             int *ci = p.cand_i + slot * kScrCap;
             int cnt = 0;

@@ -126,3 +126,74 @@ extern "C" int ebsd_quantize_crop(const void *src, int src_dtype, int64_t B, int
     EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }
+
+// ---------------------------------------------------------------------------------------- angle file (host code)
+// The text of an angle file after its two header lines -> float64 [rows][3] (latice/data_module.py:100-110: fields
+// separated by single spaces, empty fields dropped, float(token)).  Runs without the Python GIL (ctypes releases it), so
+// build_dictionary parses the angles while the GPU encodes; the Python parser needed 0.35 s per 100k rows and held the
+// GIL the launching thread needs.  Only the REGULAR case is handled here: every line exactly three plain decimal numbers,
+// nothing but spaces around them.  Anything else (short or long rows, blank lines, tabs, "nan", "1_0", non-ASCII, lone
+// carriage returns) returns -1 and the caller falls back to the Python restatement, which reproduces the reference's
+// padding and error messages.  std::from_chars is locale independent and correctly rounded, like Python's float().
+#include <charconv>
+
+namespace {
+inline bool plain_decimal(const char *b, const char *e) {
+    const char *p = b;
+    if (p < e && (*p == '+' || *p == '-')) ++p;
+    int digits = 0;
+    while (p < e && *p >= '0' && *p <= '9') ++p, ++digits;
+    if (p < e && *p == '.') {
+        ++p;
+        while (p < e && *p >= '0' && *p <= '9') ++p, ++digits;
+    }
+    if (digits == 0) return false;
+    if (p < e && (*p == 'e' || *p == 'E')) {
+        ++p;
+        if (p < e && (*p == '+' || *p == '-')) ++p;
+        int ed = 0;
+        while (p < e && *p >= '0' && *p <= '9') ++p, ++ed;
+        if (ed == 0) return false;
+    }
+    return p == e;
+}
+}  // namespace
+
+extern "C" int64_t ebsd_parse_angle_text(const char *text, size_t len, double *out, int64_t capacity_rows) {
+    if (!text || !out || capacity_rows < 0) return -1;
+    const char *p = text, *end = text + len;
+    int64_t rows = 0;
+    while (p < end) {
+        const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
+        const char *line_end = eol ? eol : end;
+        const char *le = line_end;
+        if (le > p && le[-1] == '\r' && eol) --le;   // "\r\n" (universal newlines)
+        if (rows >= capacity_rows) return -1;
+        int ntok = 0;
+        const char *q = p;
+        while (true) {
+            while (q < le && *q == ' ') ++q;
+            if (q >= le) break;
+            const char *tb = q;
+            while (q < le && *q != ' ') {
+                const unsigned char c = (unsigned char)*q;
+                if (c < 0x21 || c > 0x7e) return -1;   // tabs, control characters, lone CR, non-ASCII: generic parser
+                ++q;
+            }
+            if (ntok == 3 || !plain_decimal(tb, q)) return -1;
+            const char *fb = (*tb == '+') ? tb + 1 : tb;   // from_chars does not take a leading plus
+            double v = 0.0;
+            const std::from_chars_result r = std::from_chars(fb, q, v);
+            if (r.ec == std::errc::result_out_of_range) {
+                return -1;   // float() gives inf / 0.0 here: leave it to the generic parser
+            }
+            if (r.ec != std::errc() || r.ptr != q) return -1;
+            out[rows * 3 + ntok] = v;
+            ++ntok;
+        }
+        if (ntok != 3) return -1;
+        ++rows;
+        p = eol ? eol + 1 : end;
+    }
+    return rows;
+}

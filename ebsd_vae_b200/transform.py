@@ -90,6 +90,9 @@ def parse_rotation_angles(path: str | Path) -> np.ndarray:
     """
     path = Path(path)
     try:
+        fast = _parse_rotation_angles_native(path)
+        if fast is not None:
+            return fast
         with open(path) as fh:
             lines = fh.readlines()[2:]
         rows = [[tok for tok in line.strip().split(" ") if tok] for line in lines]
@@ -109,6 +112,30 @@ def parse_rotation_angles(path: str | Path) -> np.ndarray:
         raise
     except Exception as exc:  # noqa: BLE001 - mirrors the reference's catch-all
         raise ValueError(f"Failed to parse rotation angles file: {exc}") from exc
+
+
+def _parse_rotation_angles_native(path: Path) -> np.ndarray | None:
+    """The regular case (three plain decimal numbers per line) in C, without the GIL (``ebsd_parse_angle_text``);
+    None when the file is anything else -- the Python restatement above then reproduces the reference's behaviour."""
+    from . import _native
+
+    with open(path, "rb") as fh:
+        raw = fh.read()
+    pos = 0
+    for _ in range(2):   # the two header lines (readlines()[2:])
+        nl = raw.find(b"\n", pos)
+        if nl < 0:
+            return None
+        pos = nl + 1
+    if b"\r" in raw[:pos].replace(b"\r\n", b""):   # a lone CR would be a line break under universal newlines
+        return None
+    body = raw[pos:]
+    cap = body.count(b"\n") + 1
+    out = np.empty((cap, 3), dtype=np.float64)
+    n = _native.load().ebsd_parse_angle_text(body, len(body), out.ctypes.data, cap)
+    if n < 0:
+        return None
+    return out[:n]
 
 
 def load_patterns(path: str | Path) -> np.ndarray:

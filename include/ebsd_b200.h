@@ -72,6 +72,16 @@ int ebsd_quantize_crop(const void *src, int src_dtype, int64_t B, int H, int W, 
                        int lx, uint8_t *dst, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Angle file: the text AFTER the two header lines -> float64 [rows][3] (phi1, Phi, phi2 in degrees)
+ *   replaces the regular case of DPDataModule._parse_rotation_angles (latice/data_module.py:87-116: fields separated
+ *   by single spaces, empty fields dropped, float(token)).  Host code, no GPU; callable without the Python GIL.
+ * Returns the number of rows, or -1 when the text is not "three plain decimal numbers per line" (short / long / blank
+ * rows, tabs, nan, underscores, non-ASCII ...) or does not fit `capacity_rows`: the caller then runs its generic
+ * parser, which reproduces the reference's NaN padding and error messages (ebsd_vae_b200/transform.py).
+ * ------------------------------------------------------------------------------------------- */
+int64_t ebsd_parse_angle_text(const char *text, size_t len, double *out, int64_t capacity_rows);
+
+/* ---------------------------------------------------------------------------------------------
  * Encoder: VariationalAutoEncoderRawData.encoder + mu / logvar heads
  *   replaces latice/model.py:55-58 (forward up to logvar), layer plan latice/model.py:93-129,
  *   as called from latice/index/dp_indexer.py:133-137, 177-184, 281-287.

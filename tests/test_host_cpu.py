@@ -82,6 +82,39 @@ def test_angle_parser(golden_dir, tmp_path):
         np.testing.assert_array_equal(transform.parse_rotation_angles(f), want)
 
 
+def test_native_angle_parser_equals_python_restatement(tmp_path, monkeypatch):
+    """ebsd_parse_angle_text (host C++, no GIL) takes the regular files and returns exactly what the Python restatement
+    of latice/data_module.py:100-110 returns; anything irregular is left to that restatement (returns None)."""
+    rng = np.random.default_rng(3)
+    regular = "Euler angles\n2000\n" + "".join(
+        f"{float(a)!r} {b:.4e}   +{abs(c):.3f}  \n" for a, b, c in rng.uniform(-400, 400, (2000, 3)))
+    cases = {"regular": (regular, True), "crlf": ("h\r\nh\r\n1 2 3\r\n4 5 6\r\n", True),
+             "no_final_newline": ("h\nh\n1 2 3\n4. .5 -6e-3", True), "only_header": ("h\nh\n", True),
+             "padded": ("h\nh\n   1 2 3   \n", True), "blank_line": ("h\nh\n1 2 3\n\n", False),
+             "short_row": ("h\nh\n1 2 3\n4 5\n", False), "nan": ("h\nh\nnan 2 3\n", False),
+             "underscore": ("h\nh\n1_0 2 3\n", False), "overflow": ("h\nh\n1e999 1e-999 3\n", False),
+             "lone_cr": ("h\nh\n1 2 3\r4 5 6\n", False), "non_ascii": ("h\nh\n1 2 \u00b53\n", None)}
+    for name, (text, native) in cases.items():
+        f = tmp_path / f"{name}.txt"
+        with open(f, "w", newline="", encoding="utf-8") as fh:
+            fh.write(text)
+        fast = transform._parse_rotation_angles_native(f)
+        if native is not None:
+            assert (fast is not None) == native, name
+        with monkeypatch.context() as m:
+            m.setattr(transform, "_parse_rotation_angles_native", lambda p: None)
+            try:
+                want = transform.parse_rotation_angles(f)
+            except ValueError:
+                with pytest.raises(ValueError, match="Failed to parse rotation angles file"):
+                    m.undo()
+                    transform.parse_rotation_angles(f)
+                continue
+        np.testing.assert_array_equal(transform.parse_rotation_angles(f), want)
+        if fast is not None:
+            np.testing.assert_array_equal(fast, want)
+
+
 def test_config_defaults_match_reference():
     c = E.IndexerConfig()
     assert (c.batch_size, c.latent_dim, c.random_seed, tuple(c.image_size), c.top_n, c.orientation_threshold) == (

@@ -32,7 +32,7 @@ def run():
     _native.check(lib.ebsd_encoder_block(eng._handle, layer, 0, src.data_ptr(), src_sums.data_ptr(), hw * hw, n,
                                              raw.data_ptr(), sums.data_ptr(), st), "dbg")
 REPS = 10
-for flags in (0, 1, 2, 4, 8, 16, 1 | 2, 1 | 4, 2 | 4, 1 | 2 | 4):
+for flags in (0, 1, 2, 4, 8, 16, 32, 1 | 2, 1 | 4, 2 | 4, 1 | 2 | 4):
     lib.ebsd_profile_set_flags(flags)
     for _ in range(3): run()
     torch.cuda.synchronize()
