@@ -578,17 +578,19 @@ __global__ void __launch_bounds__(256) topk_rerank_kernel(const float *__restric
                         warp_insert<int>(e_dot, e_idx, __shfl_sync(0xffffffffu, d, j2), __shfl_sync(0xffffffffu, row, j2), lane);
                 }
             } else {
+                // the group's rows: tiles of relative parity half >> 1 in the item's range, column half (half & 1)
                 const long long tile0 = p.tile_begin + (lo - u_lo), tile1 = p.tile_begin + (hi - u_lo);
-                for (long long t = tile0; t < tile1; ++t)
+                const long long tile_first = tile0 + (((tile0 - p.tile_begin) ^ (half >> 1)) & 1);
+                for (long long t = tile_first; t < tile1; t += 2)
                     for (int c0 = 0; c0 < kScrGroupCols; c0 += 32) {
-                        const long long row = t * kScrN + half * kScrGroupCols + c0 + lane;
+                        const long long row = t * kScrN + (half & 1) * kScrGroupCols + c0 + lane;
                         const float d = row < p.N ? canonical_dot(qv, dict + row * kD) : -INFINITY;
                         const float kth = __shfl_sync(0xffffffffu, e_dot, p.k - 1);
                         unsigned mask = __ballot_sync(0xffffffffu, row < p.N && d >= kth);
                         while (mask) {
                             const int src = __ffs(mask) - 1;
                             mask &= mask - 1;
-                            warp_insert<int>(e_dot, e_idx, __shfl_sync(0xffffffffu, d, src), (int)(t * kScrN + half * kScrGroupCols + c0 + src), lane);
+                            warp_insert<int>(e_dot, e_idx, __shfl_sync(0xffffffffu, d, src), (int)(t * kScrN + (half & 1) * kScrGroupCols + c0 + src), lane);
                         }
                     }
             }

@@ -17,12 +17,15 @@
 //              Those k rows have s >= kth - EPS, so the final k-th best exact dot S_k >= kth - EPS, and a dropped row
 //              has s <= s~ + EPS < kth - EPS <= S_k: it cannot be in the top-k, ties included.
 //   layout     TMEM lane = query, column = dictionary row.  A 256-row tile is computed as two 128-column halves with
-//              their own accumulator and barriers (four accumulators = 512 TMEM columns, double-buffered per half);
-//              16 epilogue warps = 4 lane quarters x 4 column groups of 64: an epilogue thread owns one query (its
-//              threshold lives in a register) and scans 64 columns per tile, 32 per tcgen05.ld, with a 3-input max
-//              tree and one compare per chunk; survivors go to a per-(work item, column group, query) buffer of CAP
-//              entries in global memory, compacted out of line when fewer than 32 entries are free (k-th largest
-//              -> new thr).
+//              their own accumulator and barriers; four accumulators = 512 TMEM columns = (tile parity, half).
+//              16 epilogue warps = 4 lane quarters x 4 GROUPS, group g = (tile parity << 1) | half: a warp owns ONE
+//              accumulator, visits every second tile and scans all 128 columns of its half there (4 tcgen05.ld of 32
+//              columns; the barrier round trip, the address arithmetic and the loop overhead are paid once per 128
+//              columns -- with 64 columns of every tile per warp they were half of the ~100 instructions per warp and
+//              tile).  An epilogue thread owns one query (its threshold lives in a register): a 3-input max tree and
+//              one compare per chunk; survivors go to a per-(work item, group, query) buffer of CAP entries in
+//              global memory, compacted out of line when fewer than 32 entries are free (k-th largest -> new thr).
+//              Tile parity is RELATIVE to the pass (t - tile_begin), so the re-rank knows which rows a group covered.
 //   re-rank    topk_rerank_kernel: one warp per query gathers the surviving rows of all its buffers, recomputes the
 //              canonical fp32 dot and inserts into the (dot desc, row asc) sorted list of the exact kernel.
 #pragma once
@@ -40,9 +43,12 @@ constexpr int kScrTileB = kScrN * kScrRowB;   // 16 KiB
 constexpr int kScrQB = kScrM * kScrRowB;      // 8 KiB
 constexpr int kScrStages = 6;
 constexpr int kScrCap = 96;          // entries of a survivor buffer; compacted when fewer than 32 are free (CAP - 32 > EBSD_MAX_TOPK)
-constexpr int kScrGroups = 4;        // column groups of a tile (epilogue warps per TMEM lane quarter)
-constexpr int kScrGroupCols = kScrN / kScrGroups;
+constexpr int kScrGroups = 4;        // survivor groups of a work item = accumulators: (tile parity << 1) | column half
+constexpr int kScrGroupCols = kScrN / 2;   // columns a group scans in each tile of its parity
 constexpr float kScrEps = 1e-5f;
+#ifndef EBSD_SCREEN_KO
+#define EBSD_SCREEN_KO 0   // compile-time role knock-outs, timing only (tools/roles_screen.sh): 1 no max tree, 2 no TMEM loads, 4 one MMA of three
+#endif
 constexpr int kScrThreads = 128 + 128 * kScrGroups;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4.. epilogue (lane quarter x column group)
 constexpr int kScrSmem = 1024 + kScrStages * kScrTileB + kScrQB + 256;
 
@@ -173,7 +179,7 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
         mbar_init(q_empty, 1);
         for (int b = 0; b < 4; ++b) {
             mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], 2 * kScrGroups);   // the 8 warps (4 lane quarters x 2 column groups) of one half
+            mbar_init(&tempty[b], 4);   // the 4 warps (lane quarters) of the accumulator's group
         }
         mbar_fence_init();
         tma_prefetch_desc(&map_d);
@@ -205,87 +211,91 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA: s~ = q_hi.d_hi + q_hi.d_lo + q_lo.d_hi, one accumulator per dictionary tile
+        // ===================== MMA: s~ = q_hi.d_hi + q_hi.d_lo + q_lo.d_hi, one accumulator per half tile
         if (elect_one_sync()) {
             // A 256-row dictionary tile is computed as two 128-column halves with their own TMEM accumulator and
             // barriers: the epilogue warps of half 0 and of half 1 form two independent double-buffered pipelines, so
             // the MMA -> drain -> release round trip of one half overlaps the other's (with one 256-column
             // accumulator per tile the hand-off was a latency chain: ~1400 cycles per tile against a 450-cycle drain).
             constexpr uint32_t idesc = umma_idesc_f16(kScrN / 2);
-            unsigned it = 0, qit = 0, tj = 0;
+            unsigned it = 0, qit = 0, use0 = 0, use1 = 0;   // use*: tiles issued so far per relative tile parity
             for (long long u = u_begin; u < u_end; ++qit) {
                 const ScreenItem item = screen_item_at(p, blockIdx.x, u, u_end);
                 mbar_wait_bounded(q_full, qit & 1u);
                 tc_fence_after();
                 const uint32_t qa = smem_u32(smem_q);
-                for (long long t = item.tile0; t < item.tile1; ++t, ++it, ++tj) {
+                for (long long t = item.tile0; t < item.tile1; ++t, ++it) {
                     const int s = it % kScrStages;
                     mbar_wait_bounded(&d_full[s], (it / kScrStages) & 1u);
+                    const int par = (int)((t - p.tile_begin) & 1);
+                    const unsigned use = par ? use1 : use0;
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        const int buf = (int)(tj & 1) * 2 + half;
-                        mbar_wait_bounded(&tempty[buf], ((tj >> 1) & 1u) ^ 1u);
+                        const int buf = par * 2 + half;
+                        mbar_wait_bounded(&tempty[buf], (use & 1u) ^ 1u);
                         tc_fence_after();
                         const uint32_t db = smem_u32(smem_d + s * kScrTileB) + (uint32_t)(half * (kScrN / 2) * kScrRowB);
                         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * (kScrN / 2));
                         umma_f16(d_tmem, umma_smem_desc<kScrRowB>(qa), umma_smem_desc<kScrRowB>(db), idesc, 0u);            // hi.hi
+#if !(EBSD_SCREEN_KO & 4)
                         umma_f16(d_tmem, umma_smem_desc<kScrRowB>(qa), umma_smem_desc<kScrRowB>(db + 32), idesc, 1u);       // hi.lo
                         umma_f16(d_tmem, umma_smem_desc<kScrRowB>(qa + 32), umma_smem_desc<kScrRowB>(db), idesc, 1u);       // lo.hi
+#endif
                         if (half == 1) umma_commit(&d_empty[s]);
                         umma_commit(&tfull[buf]);
                     }
+                    if (par) ++use1;
+                    else ++use0;
                 }
                 umma_commit(q_empty);  // the query tile may be replaced once this item's MMAs have read it
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue: threshold filter, one thread = one query x one column group of 64
-        const int quarter = warp & 3, half = (warp - 4) >> 2;   // `half` = column group of this warp
+        // ===================== epilogue: threshold filter, one thread = one query x the 128 columns of one accumulator
+        const int quarter = warp & 3, g = (warp - 4) >> 2;   // g = accumulator = (tile parity << 1) | column half
+        const int par = g >> 1, half = g & 1;
         const int m = quarter * 32 + lane;
-        // shared-window addresses of this warp's two accumulator barriers, computed once (the generic pointers were
-        // re-derived from the aligned dynamic-smem base on every tile: ~20 of ~160 instructions per warp and tile)
+        // shared-window addresses of this warp's accumulator barriers, computed once
         // (the opaque mov keeps ptxas from rematerialising the address computation inside the loop)
-        uint32_t tfull_u32, tempty_u32;
-        asm volatile("mov.u32 %0, %1;" : "=r"(tfull_u32) : "r"(smem_u32(tfull) + (uint32_t)((half >> 1) * 8)));
-        asm volatile("mov.u32 %0, %1;" : "=r"(tempty_u32) : "r"(smem_u32(tempty) + (uint32_t)((half >> 1) * 8)));
-        unsigned tj = 0;
+        uint32_t tfull_u32, tempty_u32, t_row;
+        asm volatile("mov.u32 %0, %1;" : "=r"(tfull_u32) : "r"(smem_u32(tfull) + (uint32_t)(g * 8)));
+        asm volatile("mov.u32 %0, %1;" : "=r"(tempty_u32) : "r"(smem_u32(tempty) + (uint32_t)(g * 8)));
+        asm volatile("mov.u32 %0, %1;" : "=r"(t_row) : "r"(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * kScrGroupCols)));
+        const int nrows = p.N > 0x7fffffffll ? 0x7fffffff : (int)p.N;   // rows are 32-bit throughout (cand_i)
+        unsigned use = 0;   // tiles of this parity drained so far
         for (long long u = u_begin; u < u_end;) {
             const ScreenItem item = screen_item_at(p, blockIdx.x, u, u_end);
             const int qt = item.qt;
-            const long long tile0 = item.tile0, tile1 = item.tile1;
+            const int tile1 = (int)item.tile1;
+            const int tile_first = (int)item.tile0 + ((((int)(item.tile0 - p.tile_begin) ^ par) & 1));
             const bool live = (long long)qt * kScrM + m < p.Q;
-            const long long slot = ((long long)item.id * kScrGroups + half) * kScrM + m;
+            const long long slot = ((long long)item.id * kScrGroups + g) * kScrM + m;
             float *cs = p.cand_s + slot * kScrCap;
             int *ci = p.cand_i + slot * kScrCap;
             int cnt = 0;
             // k prefix rows have exact dots >= tau0, so S_k >= tau0; a row with s~ < tau0 - EPS has s < tau0
             float thr = live ? p.tau0[((long long)qt * kScrM + m) * p.k + (p.k - 1)] - kScrEps : INFINITY;
-            for (long long t = tile0; t < tile1; ++t, ++tj) {
-                // accumulator (tile parity, column half of the tile) = barrier index (tj & 1) * 2 + (half >> 1)
-                mbar_wait_bounded_u32(tfull_u32 + (uint32_t)((tj & 1) * 16), (tj >> 1) & 1u);
+            for (int t = tile_first; t < tile1; t += 2, ++use) {
+                mbar_wait_bounded_u32(tfull_u32, use & 1u);
                 tc_fence_after();
-                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((tj & 1) * kScrN + half * kScrGroupCols);
-                const long long row_base = t * kScrN + half * kScrGroupCols;
+                const int row_base = t * kScrN + half * kScrGroupCols;
                 // survivors of one 32-column chunk (rare).  The code is kept SMALL on purpose: the first version inlined
                 // the buffer compaction into each of the 32 unrolled steps (17k SASS instructions, far beyond the
-                // instruction cache), every entry cost ~2000 cycles of instruction fetch, and because a tile is only
-                // released when all 16 warps are done, nearly every tile paid for it (ncu: 57 % of the epilogue time
-                // waiting for the next accumulator, tools/tmem_rate.cu: the TMEM drain itself takes ~450 cycles per
-                // tile).  Now: room for a whole chunk is made up front (out of line), the steps are predicated appends.
+                // instruction cache) and every entry cost ~2000 cycles of instruction fetch.  Now: room for a whole
+                // chunk is made up front (out of line), the steps are predicated appends.
                 auto scan = [&](const float (&v)[32], int c0) {
                     if (cnt > kScrCap - 32) {
                         const float2 r = screen_compact(cs, ci, cnt, p.k);
                         thr = r.x;
                         cnt = __float_as_int(r.y);
                     }
-                    const long long row0 = row_base + c0;
-                    const long long left = p.N - row0;   // rows past the end are TMA zero fill
-                    const int nvalid = left < 32 ? (int)left : 32;
+                    const int row0 = row_base + c0;
+                    const int nvalid = nrows - row0;   // rows past the end are TMA zero fill
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         if (v[i] >= thr && i < nvalid) {
                             cs[cnt] = v[i];
-                            ci[cnt] = (int)row0 + i;
+                            ci[cnt] = row0 + i;
                             ++cnt;
                         }
                     }
@@ -301,18 +311,23 @@ topk_screen_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_const
                     }
                     return fmaxf(fmaxf(a, b), fmaxf(c, d));
                 };
-                // one 32-column chunk per round trip (two loads in flight measured slower: 59 vs 39 ms at 1M x 65536)
 #pragma unroll 1
                 for (int c0 = 0; c0 < kScrGroupCols; c0 += 32) {
                     float v[32];
+#if EBSD_SCREEN_KO & 2
+                    continue;
+#endif
                     tmem_ld32(t_row + c0, v);
                     tmem_ld_wait();
+#if EBSD_SCREEN_KO & 1
+                    if (v[0] + v[31] == 12345.678f) cnt = -1;
+                    continue;
+#endif
                     if (chunk_max(v) >= thr) scan(v, c0);   // queries past Q have thr = +inf
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0)
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_u32 + (uint32_t)((tj & 1) * 16)) : "memory");
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_u32) : "memory");
             }
             p.cand_n[slot] = cnt;
         }
