@@ -162,3 +162,17 @@ def test_weight_extraction_accepts_reference_layouts():
     assert torch.equal(m.state_dict()["encoder.13.0.weight"], sd["encoder.13.0.weight"])
     with pytest.raises(KeyError):
         E.model.extract_hot_state_dict({"foo": torch.zeros(1)})
+
+
+def test_copy_slices_cover_the_batch_with_a_short_first_slice():
+    """DiffractionPatternIndexer._copy_slices: contiguous cover of [0, b), no empty slice, nothing longer than one
+    encoder pass, and a first slice of at most half a pass once the batch is larger than that."""
+    from ebsd_vae_b200.dp_indexer import DiffractionPatternIndexer as D
+
+    for b in list(range(1, 40)) + [700, 740, 741, 1479, 1480, 1481, 2959, 2960, 2961, 8880, 10000, 12345, 100000]:
+        sl = D._copy_slices(b)
+        assert sl[0][0] == 0 and sl[-1][1] == b
+        assert all(x[1] == y[0] for x, y in zip(sl, sl[1:]))
+        assert all(0 < e - a <= D.ENCODE_PASS for a, e in sl)
+        if b > D.ENCODE_PASS // 2:
+            assert sl[0][1] - sl[0][0] <= (D.ENCODE_PASS + 1) // 2 + 1
