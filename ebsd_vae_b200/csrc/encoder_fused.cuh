@@ -835,6 +835,52 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     sbuf = (sbuf + 1) % C::NSB;
                     // plane statistics of the un-pooled output
                     if (EBSD_DBG(p) & 8) continue;
+                    if constexpr (!POOL) {
+                        // Un-pooled blocks: the warp's 32 pixels x 32 channels are already staged as a swizzled
+                        // [pixel row][channel] box for the TMA store, so lane c sums COLUMN c of it: 32 conflict-free
+                        // LDS.32 + 64 FADD/FFMA, all independent of each other, instead of two transposing shuffle
+                        // reductions (62 SHFL + ~190 ALU instructions in five dependent rounds).  The TMA store only
+                        // reads the box; the __syncwarp before the next refill orders these reads before its stores.
+                        const uint32_t col = stg + (uint32_t)((lane & 3) << 2);
+                        float s[C::NI == 1 ? 2 : C::NI], q[C::NI == 1 ? 2 : C::NI];
+#pragma unroll
+                        for (int i = 0; i < (C::NI == 1 ? 2 : C::NI); ++i) s[i] = q[i] = 0.f;
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) {
+                            const float x = lds32(col + (uint32_t)(r * 128) + (uint32_t)((((lane >> 2) ^ (r & 7))) << 4));
+                            const int a = C::NI == 1 ? (r & 1) : (r >> 4);   // NI == 2: rows 0-15 image slot 0, 16-31 slot 1
+                            s[a] += x;
+                            q[a] = fmaf(x, x, q[a]);
+                        }
+                        if (C::NI == 1) {
+                            const float t1 = s[0] + s[1], t2 = q[0] + q[1];
+                            if (TILE_FLUSH) {
+                                if (n < p.nimg) {
+                                    double *dst = p.sums + ((long long)n * COUT + cb * 32 + lane) * 2;
+                                    atomicAdd(dst, (double)t1);
+                                    atomicAdd(dst + 1, (double)t2);
+                                }
+                            } else {
+                                acc1[TILE_FLUSH ? 0 : cb][0].add(t1);
+                                acc2[TILE_FLUSH ? 0 : cb][0].add(t2);
+                            }
+                        } else {
+#pragma unroll
+                            for (int sl = 0; sl < C::NI; ++sl) {
+                                if (TILE_FLUSH) {
+                                    if (n + sl < p.nimg) {
+                                        double *dst = p.sums + ((long long)(n + sl) * COUT + cb * 32 + lane) * 2;
+                                        atomicAdd(dst, (double)s[sl]);
+                                        atomicAdd(dst + 1, (double)q[sl]);
+                                    }
+                                } else {
+                                    acc1[TILE_FLUSH ? 0 : cb][sl].add(s[sl]);
+                                    acc2[TILE_FLUSH ? 0 : cb][sl].add(q[sl]);
+                                }
+                            }
+                        }
+                        continue;
+                    }
                     if (C::NI == 1) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) w[i] = v[i] * v[i];
