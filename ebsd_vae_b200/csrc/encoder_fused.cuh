@@ -118,10 +118,17 @@ struct FusedCfg {
     static constexpr bool ACCUM = COUT == 32 && NT > 1;
     static constexpr int NSB = ACCUM ? NT : (!POOL ? (RESIDENT_B ? EBSD_NSB_RESIDENT : EBSD_NSB_STREAMED) : 1);  // staging boxes per warp
     static constexpr int STAGING = 4 * NSB * WSTG;
+    // pooled blocks: a [32 pixels][32 channels] fp32 scratch box per epilogue warp holding the UN-pooled values of the
+    // current (tile, channel block), so that the plane statistics are column sums read back with LDS (see the epilogue)
+#ifndef EBSD_POOL_STAT_LDS
+#define EBSD_POOL_STAT_LDS 1
+#endif
+    static constexpr bool STAT_LDS = EBSD_POOL_STAT_LDS != 0 && POOL && !ACCUM;
+    static constexpr int STAT_SCRATCH = STAT_LDS ? 4 * 4096 : 0;
     // barriers + tables (+ FIRST: two conv0 patches of PATCH_BYTES, written by a helper warp one item ahead) | staging
     static constexpr int PATCH_BYTES = (PATCH_H * PATCH_S * 4 + 127) / 128 * 128;
     static constexpr int XBASE = FIRST ? (2560 + 2 * PATCH_BYTES + 1023) / 1024 * 1024 : 8192;
-    static constexpr int EXTRA = XBASE + STAGING;
+    static constexpr int EXTRA = XBASE + STAGING + STAT_SCRATCH;
     static constexpr int B_FIT = (226 * 1024 - 1024 - EXTRA - A_STAGES * A_STAGE) / B_CTA;
     static constexpr int B_STAGES = RESIDENT_B ? 9 * NCHUNK : (B_FIT > 8 ? 8 : B_FIT);
     static constexpr int B_BYTES = B_STAGES * B_CTA;
@@ -639,6 +646,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         const int prow = C::NI == 1 ? ((lane >> 4) * 4 + (xl >> 1)) : (im * 4 + (xl >> 1));
         const int urow = C::NI == 1 ? lane : (im * 16 + ((lane >> 4) & 1) * 8 + xl);
         const uint32_t stg_u32 = smem_u32(extra + C::XBASE) + (uint32_t)(quarter * C::NSB * C::WSTG);
+        const uint32_t scr_u32 = smem_u32(extra + C::XBASE + C::STAGING) + (uint32_t)(quarter * 4096);   // STAT_LDS
         int sbuf = 0;
         // Running plane sums in fp64: the per-tile fp32 partial sums are fixed by the tile, but WHICH tiles of an image a
         // CTA handles depends on where the image sits in the batch -- fp32 running sums made equal patterns differ by
@@ -788,6 +796,14 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     const uint32_t stg = stg_u32 + (uint32_t)(sbuf * C::WSTG);
                     if (lane == 0) bulk_wait_read<C::NSB - 1>();
                     __syncwarp();
+                    if (C::STAT_LDS) {
+                        const uint32_t rowa = scr_u32 + (uint32_t)(lane * 128);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            sts128(rowa + (uint32_t)((i ^ (lane & 7)) << 4),
+                                   make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
+                                              __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3])));
+                    }
                     if (POOL) {
                         // transposing butterfly: after the x-pair step a lane keeps 16 channels, after the row-pair
                         // step 8 channels, each the maximum over the 2x2 block
@@ -835,20 +851,23 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     sbuf = (sbuf + 1) % C::NSB;
                     // plane statistics of the un-pooled output
                     if (EBSD_DBG(p) & 8) continue;
-                    if constexpr (!POOL) {
+                    if constexpr (!POOL || C::STAT_LDS) {
                         // Un-pooled blocks: the warp's 32 pixels x 32 channels are already staged as a swizzled
                         // [pixel row][channel] box for the TMA store, so lane c sums COLUMN c of it: 32 conflict-free
                         // LDS.32 + 64 FADD/FFMA, all independent of each other, instead of two transposing shuffle
                         // reductions (62 SHFL + ~190 ALU instructions in five dependent rounds).  The TMA store only
                         // reads the box; the __syncwarp before the next refill orders these reads before its stores.
-                        const uint32_t col = stg + (uint32_t)((lane & 3) << 2);
+                        // Pooled blocks (STAT_LDS): the same over a scratch box the un-pooled values were written to
+                        // before the pooling butterfly (row = lane).
+                        const uint32_t col = (POOL ? scr_u32 : stg) + (uint32_t)((lane & 3) << 2);
                         float s[C::NI == 1 ? 2 : C::NI], q[C::NI == 1 ? 2 : C::NI];
 #pragma unroll
                         for (int i = 0; i < (C::NI == 1 ? 2 : C::NI); ++i) s[i] = q[i] = 0.f;
 #pragma unroll
                         for (int r = 0; r < 32; ++r) {
                             const float x = lds32(col + (uint32_t)(r * 128) + (uint32_t)((((lane >> 2) ^ (r & 7))) << 4));
-                            const int a = C::NI == 1 ? (r & 1) : (r >> 4);   // NI == 2: rows 0-15 image slot 0, 16-31 slot 1
+                            // NI == 2: un-pooled box rows 0-15 = image slot 0, 16-31 = slot 1; scratch rows = lanes, slot (r >> 3) & 1
+                            const int a = C::NI == 1 ? (r & 1) : (POOL ? ((r >> 3) & 1) : (r >> 4));
                             s[a] += x;
                             q[a] = fmaf(x, x, q[a]);
                         }
