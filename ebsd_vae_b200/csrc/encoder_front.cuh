@@ -58,7 +58,8 @@ struct FrontCfg {
     static constexpr int OFF_IM = OFF_W + W_REGION;
     static constexpr int OFF_PATCH = OFF_IM + IM_BUFS * IM_BYTES;
     static constexpr int OFF_STG = OFF_PATCH + NPATCH * PATCH_STRIDE;
-    static constexpr int OFF_X = OFF_STG + STAGING;                                   // barriers (256 B) + table (256 B)
+    static constexpr int OFF_SCR = OFF_STG + STAGING;                                 // [epilogue warp][32 lanes][32 floats]: plane-sum scratch
+    static constexpr int OFF_X = OFF_SCR + 8 * 4096;                                  // barriers (256 B) + table (256 B)
     static constexpr int SMEM_BYTES = 1024 + OFF_X + 1024;
     static constexpr int ACC_COLS = NT * 64;                                          // conv1 accumulators of one item
     static constexpr int C0_COL = 2 * ACC_COLS, C0_COLS = MT * 32;                    // conv0 output: 2 buffers x MT x 32 columns
@@ -400,7 +401,29 @@ front_u8_kernel(const __grid_constant__ CUtensorMap map_pat, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);   // the accumulator is free before the (shuffle-heavy) reduction
-            if (!FRONT_DBG(p, 64)) accum.add(warp_transpose_reduce32(z, lane));
+            if (!FRONT_DBG(p, 64)) {
+                // lane c needs the sum of z[c] over the 32 lanes: through a swizzled scratch box (8 STS.128, then 32
+                // conflict-free LDS.32 + 32 FADD, all independent) instead of a transposing shuffle reduction (31 SHFL +
+                // ~120 ALU instructions in five dependent rounds -- shuffles share the shared-memory data path with the
+                // tensor core's operand reads, which is what bounds this kernel)
+                const uint32_t scr = smem_u + C::OFF_SCR + (uint32_t)((warp - 8) * 4096);
+                const uint32_t rowa = scr + (uint32_t)(lane * 128);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    sts128(rowa + (uint32_t)((i ^ (lane & 7)) << 4),
+                           make_uint4(__float_as_uint(z[4 * i]), __float_as_uint(z[4 * i + 1]), __float_as_uint(z[4 * i + 2]),
+                                      __float_as_uint(z[4 * i + 3])));
+                __syncwarp();
+                const uint32_t col = scr + (uint32_t)((lane & 3) << 2);
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int r = 0; r < 32; r += 2) {
+                    s0 += lds32(col + (uint32_t)(r * 128) + (uint32_t)(((lane >> 2) ^ (r & 7)) << 4));
+                    s1 += lds32(col + (uint32_t)((r + 1) * 128) + (uint32_t)(((lane >> 2) ^ ((r + 1) & 7)) << 4));
+                }
+                __syncwarp();   // the box is rewritten by the next item
+                accum.add(s0 + s1);
+            }
         }
         flush();
         if (lane == 0) bulk_wait_all();  // the staging buffers must outlive the TMA reads; stores complete before exit
