@@ -325,14 +325,24 @@ front_u8_kernel(const __grid_constant__ CUtensorMap map_pat, const __grid_consta
         // Eight warps: a warp reads the TMEM lane quarter warp & 3; warps 8-11 take channels 0..15 of both tiles of
         // every item, warps 12-15 channels 16..31.  (With four warps walking everything the epilogue was the longest
         // chain of the kernel: ncu showed the MMA issuer waiting for a free accumulator buffer.  Splitting by channel
-        // half rather than by tile keeps ONE transposing reduction per warp and item: warp shuffles share the
-        // shared-memory data path with the tensor core's operand reads, which is what bounds this kernel.)
+        // half rather than by tile keeps ONE plane-sum reduction per warp and item.)
         const int quarter = warp & 3, hf = (warp >> 2) & 1;
-        const int g = quarter * 4 + (lane >> 3);  // 8-row group of this lane inside the tile = image row y0 + g
-        const int xl = lane & 7;
-        const int a_par = xl & 1, b_par = g & 1;
-        const int prow = (lane >> 4) * 4 + (xl >> 1);   // pooled pixel of this lane in the warp's [2 y][4 x] box
+        // lane = pixel (image row y0 + 4 quarter + (lane >> 3), column x0 + 8 t + (lane & 7)) of tile t
         const uint32_t stg_u32 = smem_u + C::OFF_STG + (uint32_t)((hf * 4 + quarter) * C::WSTG);   // [tile][8 px x 64 B]
+        // scratch box of this warp (4 KiB): [32 rows][64 B] for the pooling, later [32 rows][128 B] for the plane sums
+        const uint32_t scr = smem_u + C::OFF_SCR + (uint32_t)((warp - 8) * 4096);
+        auto pool_pos = [](int l) { return (l & ~3) | ((l & 1) << 1) | ((l >> 1) & 1); };   // bits 0 and 1 swapped
+        const uint32_t pool_wr = scr + (uint32_t)(pool_pos(lane) * 64);
+        const uint32_t pool_wr_sw = (uint32_t)((pool_pos(lane) >> 1) & 3);
+        const int pp = lane >> 2, cc = lane & 3;   // pooled pixel ([2 y][4 x] of the warp's 4 x 8 pixels) and chunk this lane produces
+        uint32_t pool_rd[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int src = (2 * (pp >> 2) + (k >> 1)) * 8 + 2 * (pp & 3) + (k & 1);   // source lane = pixel (row, column)
+            const int pos = pool_pos(src);
+            pool_rd[k] = scr + (uint32_t)(pos * 64) + (uint32_t)((cc ^ ((pos >> 1) & 3)) << 4);
+        }
+        const uint32_t stg_off = (uint32_t)(pp * 64) + (uint32_t)((cc ^ ((pp >> 1) & 3)) << 4);
         // running plane sums as (hi, lo) fp32 pairs (PairSum, encoder_aux.cuh): lane c < 16 holds the sum of channel hf*16 + c, lane
         // 16 + c its sum of squares
         PairSum accum;
@@ -372,25 +382,30 @@ front_u8_kernel(const __grid_constant__ CUtensorMap map_pat, const __grid_consta
                     z[i] += v[i];
                     z[16 + i] = fmaf(v[i], v[i], z[16 + i]);
                 }
-                // 2x2 max: transposing butterfly, 16 -> 8 -> 4 channels per lane
-                float r[8], o[4];
+                // 2x2 max-pool THROUGH SHARED MEMORY: every lane parks its pixel's 16 channels in the warp's scratch box
+                // (4 STS.128), then lane (pooled pixel pp, 16-byte chunk cc) fetches that chunk of the four source pixels
+                // (4 LDS.128), takes 12 maxima and stores straight into the TMA staging box.  The transposing shuffle
+                // butterfly this replaces (12 SHFL + 24 selects + 12 maxima) cost twice the instructions; rows sit at
+                // position P(lane) = lane with bits 0 and 1 swapped so that the two pooled pixels of a store phase and
+                // of a load phase fall into different halves of the 32 banks.
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float send = a_par ? v[i] : v[8 + i];
-                    const float keep = a_par ? v[8 + i] : v[i];
-                    r[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
-                }
+                for (int c = 0; c < 4; ++c)
+                    sts128(pool_wr + (uint32_t)((c ^ pool_wr_sw) << 4),
+                           make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]),
+                                      __float_as_uint(v[4 * c + 3])));
+                __syncwarp();
+                float4 o = lds128(pool_rd[0]);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float send = b_par ? r[i] : r[4 + i];
-                    const float keep = b_par ? r[4 + i] : r[i];
-                    o[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+                for (int k = 1; k < 4; ++k) {
+                    const float4 x = lds128(pool_rd[k]);
+                    o.x = fmaxf(o.x, x.x);
+                    o.y = fmaxf(o.y, x.y);
+                    o.z = fmaxf(o.z, x.z);
+                    o.w = fmaxf(o.w, x.w);
                 }
                 // one box per (tile, 16-channel half): 8 pooled pixels x 64 B, 64B-swizzled
                 const uint32_t stg = stg_u32 + (uint32_t)(t * 512);
-                const int ch = a_par * 2 + b_par;  // 16-byte chunk of this lane's 4 channels inside the half
-                sts128(stg + (uint32_t)(prow * 64) + (uint32_t)((ch ^ ((prow >> 1) & 3)) << 4),
-                       make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])));
+                sts128(stg + stg_off, make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
@@ -406,7 +421,6 @@ front_u8_kernel(const __grid_constant__ CUtensorMap map_pat, const __grid_consta
                 // conflict-free LDS.32 + 32 FADD, all independent) instead of a transposing shuffle reduction (31 SHFL +
                 // ~120 ALU instructions in five dependent rounds -- shuffles share the shared-memory data path with the
                 // tensor core's operand reads, which is what bounds this kernel)
-                const uint32_t scr = smem_u + C::OFF_SCR + (uint32_t)((warp - 8) * 4096);
                 const uint32_t rowa = scr + (uint32_t)(lane * 128);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
