@@ -647,6 +647,18 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         const int urow = C::NI == 1 ? lane : (im * 16 + ((lane >> 4) & 1) * 8 + xl);
         const uint32_t stg_u32 = smem_u32(extra + C::XBASE) + (uint32_t)(quarter * C::NSB * C::WSTG);
         const uint32_t scr_u32 = smem_u32(extra + C::XBASE + C::STAGING) + (uint32_t)(quarter * 4096);   // STAT_LDS
+        auto scr_key = [](int l) { return ((l & 1) << 2) | ((l >> 1) & 3); };   // swizzle key of scratch row l
+        // STAT_LDS pooling: this lane produces chunks 2 cq, 2 cq + 1 (8 channels) of pooled pixel pp = staging row pp;
+        // its four source pixels are scratch rows (= lanes) src_k
+        const int pool_pp = lane >> 2, pool_cq = lane & 3;
+        uint32_t pool_row[4], pool_key[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int src = C::NI == 1 ? (2 * (pool_pp >> 2) + (k >> 1)) * 8 + 2 * (pool_pp & 3) + (k & 1)
+                                       : (k >> 1) * 16 + (pool_pp >> 2) * 8 + 2 * (pool_pp & 3) + (k & 1);
+            pool_row[k] = scr_u32 + (uint32_t)(src * 128);
+            pool_key[k] = (uint32_t)scr_key(src);
+        }
         int sbuf = 0;
         // Running plane sums in fp64: the per-tile fp32 partial sums are fixed by the tile, but WHICH tiles of an image a
         // CTA handles depends on where the image sits in the batch -- fp32 running sums made equal patterns differ by
@@ -797,14 +809,36 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     if (lane == 0) bulk_wait_read<C::NSB - 1>();
                     __syncwarp();
                     if (C::STAT_LDS) {
+                        // un-pooled values -> scratch row `lane`, 16-byte chunks XOR-swizzled with scr_key(lane): the
+                        // eight lanes of a store phase cover all banks, and so do the two pooled pixels (source rows
+                        // two apart) of a load phase below
                         const uint32_t rowa = scr_u32 + (uint32_t)(lane * 128);
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            sts128(rowa + (uint32_t)((i ^ (lane & 7)) << 4),
+                            sts128(rowa + (uint32_t)((i ^ scr_key(lane)) << 4),
                                    make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
                                               __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3])));
-                    }
-                    if (POOL) {
+                        // 2x2 max-pool through the scratch box: lane (pooled pixel pp, chunk pair cq) fetches its two
+                        // 16-byte chunks of the four source pixels (8 LDS.128), 24 maxima, two stores into the TMA
+                        // staging box -- the transposing shuffle butterfly (24 SHFL + 48 selects + 24 maxima) cost
+                        // three times the instructions
+                        __syncwarp();
+                        const uint32_t rowp = stg + (uint32_t)(pool_pp * 128);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            float4 o = lds128(pool_row[0] + (uint32_t)(((2 * pool_cq + e) ^ pool_key[0]) << 4));
+#pragma unroll
+                            for (int k = 1; k < 4; ++k) {
+                                const float4 x = lds128(pool_row[k] + (uint32_t)(((2 * pool_cq + e) ^ pool_key[k]) << 4));
+                                o.x = fmaxf(o.x, x.x);
+                                o.y = fmaxf(o.y, x.y);
+                                o.z = fmaxf(o.z, x.z);
+                                o.w = fmaxf(o.w, x.w);
+                            }
+                            sts128(rowp + (uint32_t)(((2 * pool_cq + e) ^ (pool_pp & 7)) << 4),
+                                   make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
+                        }
+                    } else if (POOL) {
                         // transposing butterfly: after the x-pair step a lane keeps 16 channels, after the row-pair
                         // step 8 channels, each the maximum over the 2x2 block
                         float r[16], o[8];
@@ -865,7 +899,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                         for (int i = 0; i < (C::NI == 1 ? 2 : C::NI); ++i) s[i] = q[i] = 0.f;
 #pragma unroll
                         for (int r = 0; r < 32; ++r) {
-                            const float x = lds32(col + (uint32_t)(r * 128) + (uint32_t)((((lane >> 2) ^ (r & 7))) << 4));
+                            const float x = lds32(col + (uint32_t)(r * 128) + (uint32_t)((((lane >> 2) ^ (POOL ? scr_key(r) : (r & 7)))) << 4));
                             // NI == 2: un-pooled box rows 0-15 = image slot 0, 16-31 = slot 1; scratch rows = lanes, slot (r >> 3) & 1
                             const int a = C::NI == 1 ? (r & 1) : (POOL ? ((r >> 3) & 1) : (r >> 4));
                             s[a] += x;
