@@ -424,7 +424,10 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
             // items ahead (the producers themselves run up to A_STAGES items ahead of the MMAs).  Measured on one box, whole
             // bench step: PF = 8: 223 k patterns/s, 4: 225-229 k, 2: 233 k, 1: 231-234 k, 0: 224-226 k -- windows prefetched
             // too early are evicted again by the blocks' own output stream before the producers read them
-            constexpr int PF = 2;
+#ifndef EBSD_PF
+#define EBSD_PF 2
+#endif
+            constexpr int PF = EBSD_PF;
             auto prefetch_item = [&](int item) {
                 if (C::FIRST || item >= item_end || item >= p.nitems) return;
                 int n, y0, x0;
@@ -1106,11 +1109,30 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     }
                 }
             };
+            // Thread-constant geometry.  Unit slot k of a thread is u = ptid + PRODUCERS k; when PRODUCERS is a multiple of
+            // C8 * PITCH (blocks 3-7: 320 = 8 channel groups x 10 window columns x 4 rows) the channel group and the window
+            // column of a thread never change and its window row advances by a constant per slot, so the divisions by
+            // C8 and PITCH, done twice per unit (issue and consume), drop out of the loop: the producers of these blocks
+            // are bound by their own instruction stream (block 3 alone: 660 us with MMAs and epilogue idle, 435 us with
+            // the conversion skipped as well).
+            constexpr bool FIXED_GEOM = C::NI == 1 && C::PRODUCERS % (C8 * C::PITCH) == 0;
+            constexpr int SLOT_ROWS = C::PRODUCERS / (C8 * C::PITCH);
+            const int fg_c8 = ptid % C8, fg_wx = (ptid / C8) % C::PITCH, fg_wy0 = ptid / (C8 * C::PITCH);
             // geometry of unit u of the stage (item, cc): window position, channel group, source pointer (or null)
-            auto geom = [&](int n, int y0, int x0, int cc, int u, int &pos, int &c8, int &s) -> const float * {
-                pos = u / C8;
-                c8 = u - pos * C8;
-                const int wy = pos / C::PITCH, wx = pos - wy * C::PITCH;
+            auto geom = [&](int n, int y0, int x0, int cc, int k, int &pos, int &c8, int &s) -> const float * {
+                const int u = ptid + C::PRODUCERS * k;   // k = unit slot of this thread
+                int wy, wx;
+                if constexpr (FIXED_GEOM) {
+                    c8 = fg_c8;
+                    wx = fg_wx;
+                    wy = fg_wy0 + SLOT_ROWS * k;
+                    pos = wy * C::PITCH + wx;
+                } else {
+                    pos = u / C8;
+                    c8 = u - pos * C8;
+                    wy = pos / C::PITCH;
+                    wx = pos - wy * C::PITCH;
+                }
                 int nn, y, x;
                 if (C::NI == 1) {
                     s = 0;
@@ -1132,7 +1154,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 #pragma unroll
                 for (int i = 0; i < BATCH; ++i) {
                     int pos, c8, s;
-                    const float *src = geom(n, y0, x0, c.cc, ptid + C::PRODUCERS * (c.b * BATCH + i), pos, c8, s);
+                    const float *src = geom(n, y0, x0, c.cc, c.b * BATCH + i, pos, c8, s);
                     if (src) {
                         buf[i][0] = __ldg((const float4 *)src);
                         buf[i][1] = __ldg((const float4 *)src + 1);
@@ -1146,7 +1168,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 for (int i = 0; i < BATCH; ++i) {
                     const int u = ptid + C::PRODUCERS * (c.b * BATCH + i);
                     int pos, c8, s;
-                    const float *src = geom(n, y0, x0, c.cc, u, pos, c8, s);
+                    const float *src = geom(n, y0, x0, c.cc, c.b * BATCH + i, pos, c8, s);
                     if (u >= UNITS) continue;
                     uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
                     if (src) {
