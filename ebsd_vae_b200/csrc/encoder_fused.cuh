@@ -332,6 +332,16 @@ __device__ __forceinline__ void norm_split8(const float (&x)[8], uint32_t tab_u3
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// the same with the four table entries already in registers (a thread whose channel group never changes)
+__device__ __forceinline__ void norm_split8_t(const float (&x)[8], const float4 (&tt)[4], uint4 &hi, uint4 &lo) {
+    __half2 h[4];
+    uint32_t l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) norm_split_pair(make_float2(x[2 * j], x[2 * j + 1]), tt[j], h[j], l[j]);
+    hi = *(const uint4 *)h;
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 template <class C>
 __device__ __forceinline__ void store_chunk(uint32_t stage_u32, int pos, int c8, const uint4 &hi, const uint4 &lo) {
     const uint32_t a_hi = stage_u32 + pos * C::ROWB + c8 * 16;
@@ -1164,6 +1174,11 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
             auto consume = [&](const Cursor &c, float4 (&buf)[BATCH][2], uint32_t stage_u32) {
                 int n, y0, x0;
                 decode(c.item, n, y0, x0);
+                float4 tt[4];   // FIXED_GEOM: one table read per batch instead of one per unit
+                if constexpr (FIXED_GEOM) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) tt[j] = lds128(tab_u32 + (uint32_t)((c.cc * C8 + fg_c8) * 16) + (uint32_t)j * (CIN * 2));
+                }
 #pragma unroll
                 for (int i = 0; i < BATCH; ++i) {
                     const int u = ptid + C::PRODUCERS * (c.b * BATCH + i);
@@ -1174,7 +1189,8 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                     if (src) {
                         const float xv[8] = {buf[i][0].x, buf[i][0].y, buf[i][0].z, buf[i][0].w,
                                              buf[i][1].x, buf[i][1].y, buf[i][1].z, buf[i][1].w};
-                        norm_split8(xv, tab_u32 + (uint32_t)(s * CIN * 8 + (c.cc * C8 + c8) * 16), CIN * 2, hi, lo);
+                        if constexpr (FIXED_GEOM) norm_split8_t(xv, tt, hi, lo);
+                        else norm_split8(xv, tab_u32 + (uint32_t)(s * CIN * 8 + (c.cc * C8 + c8) * 16), CIN * 2, hi, lo);
                     }
                     store_chunk<C>(stage_u32, pos, c8, hi, lo);
                 }
