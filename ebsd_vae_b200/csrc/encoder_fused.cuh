@@ -432,10 +432,12 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         // ===================== weight loads (TMA) + L2 prefetch of the windows the producers will read
         if (elect_one_sync()) {
             // items ahead (the producers themselves run up to A_STAGES items ahead of the MMAs).  Measured on one box, whole
-            // bench step: PF = 8: 223 k patterns/s, 4: 225-229 k, 2: 233 k, 1: 231-234 k, 0: 224-226 k -- windows prefetched
-            // too early are evicted again by the blocks' own output stream before the producers read them
+            // bench step, round 1: PF = 8: 223 k patterns/s, 4: 225-229 k, 2: 233 k, 1: 231-234 k, 0: 224-226 k -- windows
+            // prefetched too early are evicted again by the blocks' own output stream before the producers read them.
+            // Round 2 (leaner producers): PF = 1 beats 2 by 0.5 % on the step (292.5 vs 290.9 k; 32->64 block 451 -> 439 us),
+            // 3 and 4 lose 1-10 % on the 64x64 blocks.
 #ifndef EBSD_PF
-#define EBSD_PF 2
+#define EBSD_PF 1
 #endif
             constexpr int PF = EBSD_PF;
             auto prefetch_item = [&](int item) {
