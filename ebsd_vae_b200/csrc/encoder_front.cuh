@@ -66,6 +66,11 @@ struct FrontCfg {
     static constexpr int TMEM_COLS = 512;
     static constexpr int THREADS = 640, PRODUCER_WARPS = 8, EPILOGUE_WARPS = 8;
     static constexpr int ITEMS_X = 128 / (8 * NT), ITEMS_PER_IMAGE = (128 / 16) * ITEMS_X;   // 8 x 8
+#ifndef EBSD_FRONT_ZGROUP
+#define EBSD_FRONT_ZGROUP 4
+#endif
+    static constexpr int ZGROUP = EBSD_FRONT_ZGROUP;   // items whose per-lane plane sums are reduced together
+    static_assert(ITEMS_PER_IMAGE % ZGROUP == 0, "plane-sum groups must not straddle images");
     static_assert(C0_COL + 2 * C0_COLS <= TMEM_COLS, "TMEM budget");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(A16_BYTES % 1024 == 0 && A8_BYTES % 1024 == 0 && W16_TAP % 1024 == 0 && W8_TAP % 1024 == 0 &&
@@ -186,7 +191,10 @@ front_u8_kernel(const __grid_constant__ CUtensorMap map_pat, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int per_cta = (p.nitems + (int)gridDim.x - 1) / (int)gridDim.x;
+    // a multiple of ZGROUP items per CTA: the epilogue reduces its per-lane plane sums once per aligned group of ZGROUP
+    // items, and which items share a group must not depend on where an image sits in the batch (ITEMS_PER_IMAGE = 64 is
+    // a multiple as well, so a group never straddles an image or a CTA range)
+    const int per_cta = ((p.nitems + (int)gridDim.x - 1) / (int)gridDim.x + C::ZGROUP - 1) / C::ZGROUP * C::ZGROUP;
     const int item_begin = (int)blockIdx.x * per_cta;
     const int item_end = item_begin + per_cta < p.nitems ? item_begin + per_cta : p.nitems;
     const int n_items = item_end > item_begin ? item_end - item_begin : 0;
@@ -353,6 +361,9 @@ front_u8_kernel(const __grid_constant__ CUtensorMap map_pat, const __grid_consta
                 atomicAdd(p.sums + ((long long)cur_n * COUT + hf * 16 + (lane & 15)) * 2 + (lane >> 4), accum.value());
             accum.clear();
         };
+        float z[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) z[i] = 0.f;
         for (int j = 0; j < n_items; ++j) {
             const int buf = j & 1;
             int n, y0, x0;
@@ -367,9 +378,11 @@ front_u8_kernel(const __grid_constant__ CUtensorMap map_pat, const __grid_consta
             // both boxes of the previous item have been read by their TMA stores before they are overwritten
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
-            float z[32];  // [0,16): sums, [16,32): sums of squares of this warp's channels over its rows of both tiles
+            // z: [0,16) sums, [16,32) sums of squares of this warp's channels over its rows of the tiles of ZGROUP items
+            if (((item_begin + j) % C::ZGROUP) == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) z[i] = 0.f;
+                for (int i = 0; i < 32; ++i) z[i] = 0.f;
+            }
 #pragma unroll 1
             for (int t = 0; t < (FRONT_DBG(p, 64) ? 0 : C::NT); ++t) {
                 float v[16], w[16];
@@ -416,7 +429,7 @@ front_u8_kernel(const __grid_constant__ CUtensorMap map_pat, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);   // the accumulator is free before the (shuffle-heavy) reduction
-            if (!FRONT_DBG(p, 64)) {
+            if (!FRONT_DBG(p, 64) && (((item_begin + j) % C::ZGROUP) == C::ZGROUP - 1 || j == n_items - 1)) {
                 // lane c needs the sum of z[c] over the 32 lanes: through a swizzled scratch box (8 STS.128, then 32
                 // conflict-free LDS.32 + 32 FADD, all independent) instead of a transposing shuffle reduction (31 SHFL +
                 // ~120 ALU instructions in five dependent rounds -- shuffles share the shared-memory data path with the
