@@ -162,7 +162,12 @@ struct ConsensusParams {
     int *ref_iter;
 };
 
-__global__ void __launch_bounds__(256) consensus_kernel(const ConsensusParams p) {
+// Resident blocks per SM: the kernel is a chain of fp64 latencies (divisions, square roots, acos / atan2) with one warp
+// per query, so its speed is the number of resident warps.  Uncapped it needs 132 registers = ONE block of 8 warps per SM.
+#ifndef EBSD_CONSENSUS_MINBLOCKS
+#define EBSD_CONSENSUS_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, EBSD_CONSENSUS_MINBLOCKS) consensus_kernel(const ConsensusParams p) {
     const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (q >= p.Q) return;
