@@ -664,20 +664,26 @@ struct ScreenPlan {
     size_t off_dpairs, off_qpairs, off_cs, off_ci, off_cn, off_parts, bytes;
 };
 
+// Fewest rows of the CUDA-core seeding search, and the smallest prefix a further screen level is added for.  The seed
+// costs ~0.2 ms per 1024 rows at 80 k queries (0.83 ms of a 2.7 ms search of a 100 k-row shard with 4096 rows), an
+// extra level only a short screen pass plus one re-rank launch (~0.2 ms at 80 k queries, 0.03 ms at 10 k).
+constexpr long long kScreenSeedMinRows = 512;
+constexpr long long kScreenLevelMinRows = 1024;
+
 // Rows of the seeding search.  With tau0 the k-th best of N/8 rows a query keeps about 8k survivors over the whole
 // dictionary (k / n0 per row), spread over its (splits x column groups) buffers: the CAP-entry buffers practically
 // never fill, so the costly in-place compaction stays an exception; the seeding search itself costs 1/8 of a
 // CUDA-core search.  (N/16 measured slower: 41.7 vs 34.6 ms at 1M x 65536 -- twice the survivors, and every survivor
 // makes its whole warp walk the 32-column chunk.)
 static long long screen_prefix_rows(long long N) {
-    long long n0 = N / 8;   // called with N = the rows of stage B (N/8 of the dictionary): n0 = N/64
-    if (n0 < 4096) n0 = 4096;
+    long long n0 = N / 8;   // called with N = the rows of the first screen pass
+    if (n0 < kScreenSeedMinRows) n0 = kScreenSeedMinRows;
     return n0 < N ? n0 : N;
 }
 
 // Stage boundaries of the screen in 256-row tiles, ascending: [0] = rows of the exact CUDA-core seeding search (not
 // tile aligned), then the END tile of every screen pass; each pass covers 8x the rows of the one before
-// (N/512, N/64, N/8, N -- as many levels as keep the seed at >= 4096 rows).  The CUDA-core search costs ~12 ns per
+// (..., N/512, N/64, N/8, N -- as many levels as leave a prefix of >= 1024 rows; the seed is >= 512 rows).  The CUDA-core search costs ~12 ns per
 // row and 10k queries against ~1 ns for the screen, so it should only ever see a few thousand rows: at 1.25 M x 80 k
 // (one shard of the 10 M-row dictionary on 8 GPUs) the N/64 seed alone was 2 of 16.8 ms.
 // EBSD_TOPK_SCREEN_LEVELS=n caps the number of screen passes (A/B timing; 2 = the round-1 staging).
@@ -697,7 +703,7 @@ static ScreenStages screen_stages(long long N) {
     int n = 0;
     ends[n++] = total_tiles;
     long long rows = N;
-    while (n < max_levels && rows / 8 >= 8192) {
+    while (n < max_levels && rows / 8 >= kScreenLevelMinRows) {
         rows /= 8;
         ends[n++] = (rows + kScrN - 1) / kScrN;
     }
