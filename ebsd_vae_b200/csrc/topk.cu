@@ -528,6 +528,53 @@ __device__ __forceinline__ float canonical_dot(const float4 (&q)[4], const float
     return a;
 }
 
+// Threshold seed of the screen (run_screen): the k-th largest canonical dot of every query over the first n0 <= 512
+// rows, written to out_dot[q][k - 1] -- the only entry the first screen pass reads (its re-rank rebuilds the lists from
+// the survivors).  One warp per query, 8 or 16 rows per lane, k rounds of (lane maximum, warp maximum, the lowest owning lane
+// drops ONE occurrence): no sorted lists, no insertions.  The tiled CUDA-core kernel spends its time there on such a
+// short prefix (every query inserts k (1 + ln(n0 / k)) ~ 50 rows before its threshold bites): 376 us for 512 rows x
+// 80 k queries, 0.83 ms for 4096 rows.
+constexpr int kSeedRowsMax = 512;
+template <int R>   // rows per lane: n0 <= 32 R
+__global__ void __launch_bounds__(256) topk_seed_kth_kernel(const float *__restrict__ dict, int n0,
+                                                            const float *__restrict__ queries, long long Q, int k,
+                                                            float *__restrict__ out_dot) {
+    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    float4 qv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) qv[c] = __ldg((const float4 *)(queries + q * kD) + c);
+    float d[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const int row = j * 32 + lane;
+        d[j] = row < n0 ? canonical_dot(qv, dict + (long long)row * kD) : -INFINITY;
+    }
+    float kth = -INFINITY;
+    for (int t = 0; t < k; ++t) {
+        float m = d[0];
+#pragma unroll
+        for (int j = 1; j < R; ++j) m = fmaxf(m, d[j]);
+        float w = m;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
+        kth = w;
+        const unsigned owners = __ballot_sync(0xffffffffu, m == w);
+        if (lane == __ffs(owners) - 1) {   // drop one occurrence (duplicates count separately)
+            bool done = false;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                if (!done && d[j] == w) {
+                    d[j] = -INFINITY;
+                    done = true;
+                }
+            }
+        }
+    }
+    if (lane == 0) out_dot[q * k + (k - 1)] = kth;   // -inf when n0 < k: every row passes the first screen pass
+}
+
 // init_from_out: the output arrays already hold the exact top-k of the rows below the pass (global indices); they
 // seed the list, so the result is the top-k over both ranges.
 __global__ void __launch_bounds__(256) topk_rerank_kernel(const float *__restrict__ dict, const float *__restrict__ queries,
@@ -667,7 +714,7 @@ struct ScreenPlan {
 // Fewest rows of the CUDA-core seeding search, and the smallest prefix a further screen level is added for.  The seed
 // costs ~0.2 ms per 1024 rows at 80 k queries (0.83 ms of a 2.7 ms search of a 100 k-row shard with 4096 rows), an
 // extra level only a short screen pass plus one re-rank launch (~0.2 ms at 80 k queries, 0.03 ms at 10 k).
-constexpr long long kScreenSeedMinRows = 512;
+constexpr long long kScreenSeedMinRows = 256;
 constexpr long long kScreenLevelMinRows = 1024;
 
 // Rows of the seeding search.  With tau0 the k-th best of N/8 rows a query keeps about 8k survivors over the whole
@@ -683,7 +730,7 @@ static long long screen_prefix_rows(long long N) {
 
 // Stage boundaries of the screen in 256-row tiles, ascending: [0] = rows of the exact CUDA-core seeding search (not
 // tile aligned), then the END tile of every screen pass; each pass covers 8x the rows of the one before
-// (..., N/512, N/64, N/8, N -- as many levels as leave a prefix of >= 1024 rows; the seed is >= 512 rows).  The CUDA-core search costs ~12 ns per
+// (..., N/512, N/64, N/8, N -- as many levels as leave a prefix of >= 1024 rows; the seed is >= 256 rows).  The CUDA-core search costs ~12 ns per
 // row and 10k queries against ~1 ns for the screen, so it should only ever see a few thousand rows: at 1.25 M x 80 k
 // (one shard of the 10 M-row dictionary on 8 GPUs) the N/64 seed alone was 2 of 16.8 ms.
 // EBSD_TOPK_SCREEN_LEVELS=n caps the number of screen passes (A/B timing; 2 = the round-1 staging).
@@ -953,8 +1000,16 @@ static int run_screen(const float *dict, long long N, long long index_base, cons
         configured[dev] = true;
     }
     const ScreenStages stages = screen_stages(N);
-    if ((rc = run_exact(dict, stages.seed_rows, index_base, queries, Q, k, out_dot, out_idx, nullptr, ws + pl.off_parts, sms, st)))
+    if (stages.seed_rows <= kSeedRowsMax) {
+        if (stages.seed_rows <= 256)
+            topk_seed_kth_kernel<8><<<(unsigned)((Q + 7) / 8), 256, 0, st>>>(dict, (int)stages.seed_rows, queries, Q, k, out_dot);
+        else
+            topk_seed_kth_kernel<16><<<(unsigned)((Q + 7) / 8), 256, 0, st>>>(dict, (int)stages.seed_rows, queries, Q, k, out_dot);
+        EBSD_LAUNCH_CHECK();
+    } else if ((rc = run_exact(dict, stages.seed_rows, index_base, queries, Q, k, out_dot, out_idx, nullptr, ws + pl.off_parts,
+                               sms, st))) {
         return rc;
+    }
     auto pass = [&](long long tile_begin, long long tile_end, int init_from_out) -> int {
         ScreenParams p;
         p.Q = Q;
