@@ -599,11 +599,11 @@ __global__ void __launch_bounds__(256) topk_rerank_kernel(const float *__restric
     __syncwarp();
     // the items of this query tile: the CTAs whose unit spans intersect [qt T, (qt + 1) T) (ScreenParams)
     const long long T = p.tile_end - p.tile_begin, u_lo = (long long)qt * T, u_hi = u_lo + T;
-    long long c = u_lo * p.n_ctas / ((long long)p.n_qtiles * T);
-    while (c > 0 && screen_span_begin(p, c) > u_lo) --c;
-    while (c + 1 < p.n_ctas && screen_span_begin(p, c + 1) <= u_lo) ++c;
+    long long c = screen_span_owner(p, u_lo);
+    long long s1 = screen_span_begin(p, c);
     for (; c < p.n_ctas; ++c) {
-        const long long s0 = screen_span_begin(p, c), s1 = screen_span_begin(p, c + 1);
+        const long long s0 = s1;
+        s1 = s0 + p.span_base + (c < p.span_rem ? 1 : 0);
         if (s0 >= u_hi) break;
         const long long lo = s0 > u_lo ? s0 : u_lo, hi = s1 < u_hi ? s1 : u_hi;
         if (lo >= hi) continue;   // a CTA without units (fewer units than CTAs)
@@ -1021,6 +1021,8 @@ static int run_screen(const float *dict, long long N, long long index_base, cons
         const long long units = (long long)p.n_qtiles * (tile_end - tile_begin);
         const int grid = units < sms ? (int)(units < 1 ? 1 : units) : sms;
         p.n_ctas = grid;
+        p.span_base = units > 0 ? units / grid : 0;
+        p.span_rem = units > 0 ? (int)(units % grid) : 0;
         p.tau0 = out_dot;
         p.cand_s = (float *)(ws + pl.off_cs);
         p.cand_i = (int *)(ws + pl.off_ci);

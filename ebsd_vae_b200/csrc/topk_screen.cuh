@@ -53,16 +53,20 @@ constexpr int kScrThreads = 128 + 128 * kScrGroups;   // warp 0 TMA, 1 MMA, 2 TM
 constexpr int kScrSmem = 1024 + kScrStages * kScrTileB + kScrQB + 256;
 
 // Work distribution.  A pass covers the dictionary tiles [tile_begin, tile_end) for every query tile: U = n_qtiles * T
-// (query tile, dictionary tile) units, query-tile major.  CTA c of n_ctas takes the contiguous span
-// [c U / n_ctas, (c + 1) U / n_ctas) -- every CTA gets the same number of units to within one (with whole (query tile,
-// dictionary split) items dealt round-robin, 316 items on 148 CTAs left 29 % of the kernel idle at 10 M x 10 k) -- and
-// walks it as ITEMS = maximal pieces inside one query tile.  Along the chain of CTAs either the CTA or the query tile
+// (query tile, dictionary tile) units, query-tile major.  CTA c of n_ctas takes the contiguous span that starts at
+// c * span_base + min(c, span_rem) with span_base = U / n_ctas, span_rem = U % n_ctas (host side) -- every CTA gets the
+// same number of units to within one (with whole (query tile, dictionary split) items dealt round-robin, 316 items on
+// 148 CTAs left 29 % of the kernel idle at 10 M x 10 k), and neither the screen nor the re-rank divides by run-time
+// 64-bit values to find a span (the re-rank used ~9 such divisions per query: a quarter of its instructions).  A CTA
+// walks its span as ITEMS = maximal pieces inside one query tile.  Along the chain of CTAs either the CTA or the query tile
 // advances from one item to the next, so `cta + qt` numbers the items uniquely (< n_ctas + n_qtiles): that is the
 // slot of the item's survivor buffers, which the re-rank finds again with the same arithmetic.
 struct ScreenParams {
     long long Q, N;
     int k;
     int n_qtiles, n_ctas;
+    long long span_base;   // units per CTA (floor)
+    int span_rem;          // the first span_rem CTAs take one unit more
     long long tile_begin, tile_end;   // dictionary tiles (256 rows each) this pass covers
     const float *tau0;  // [Q][k]: exact top-k dots of a dictionary prefix (column k-1 seeds the threshold)
     float *cand_s;      // [items][groups][128][CAP] approximate dots
@@ -75,8 +79,14 @@ struct ScreenItem {
     long long tile0, tile1;   // absolute dictionary tiles
 };
 __host__ __device__ inline long long screen_span_begin(const ScreenParams &p, long long cta) {
-    const long long units = (long long)p.n_qtiles * (p.tile_end - p.tile_begin);
-    return cta * units / p.n_ctas;
+    return cta * p.span_base + (cta < p.span_rem ? cta : (long long)p.span_rem);
+}
+// the CTA whose span holds unit u (one division by the 32-bit-sized span length)
+__host__ __device__ inline long long screen_span_owner(const ScreenParams &p, long long u) {
+    const long long big = (long long)p.span_rem * (p.span_base + 1);   // units held by the longer spans
+    const long long num = u < big ? u : u - big, den = u < big ? p.span_base + 1 : (p.span_base > 0 ? p.span_base : 1);
+    const long long quo = ((num | den) >> 32) == 0 ? (long long)((unsigned)num / (unsigned)den) : num / den;
+    return u < big ? quo : p.span_rem + quo;
 }
 // the item that starts at unit u of CTA `cta`'s span [.., u_end); advances u past it
 __device__ __forceinline__ ScreenItem screen_item_at(const ScreenParams &p, int cta, long long &u, long long u_end) {

@@ -6,7 +6,20 @@ import itertools
 
 
 def span_begin(c, n_qtiles, T, n_ctas):
-    return c * (n_qtiles * T) // n_ctas
+    """screen_span_begin: the first U % n_ctas CTAs take one unit more than U // n_ctas."""
+    units = n_qtiles * T
+    base, rem = units // n_ctas, units % n_ctas
+    return c * base + min(c, rem)
+
+
+def span_owner(u, n_qtiles, T, n_ctas):
+    """screen_span_owner: the CTA whose span holds unit u."""
+    units = n_qtiles * T
+    base, rem = units // n_ctas, units % n_ctas
+    big = rem * (base + 1)
+    if u < big:
+        return u // (base + 1)
+    return rem + (u - big) // max(base, 1)
 
 
 def screen_items(n_qtiles, T, n_ctas):
@@ -28,11 +41,8 @@ def screen_items(n_qtiles, T, n_ctas):
 def rerank_items(qt, n_qtiles, T, n_ctas):
     """What topk_rerank_kernel enumerates for a query of tile qt: (id, t0, t1)."""
     u_lo, u_hi = qt * T, (qt + 1) * T
-    c = u_lo * n_ctas // (n_qtiles * T)
-    while c > 0 and span_begin(c, n_qtiles, T, n_ctas) > u_lo:
-        c -= 1
-    while c + 1 < n_ctas and span_begin(c + 1, n_qtiles, T, n_ctas) <= u_lo:
-        c += 1
+    c = span_owner(u_lo, n_qtiles, T, n_ctas)
+    assert span_begin(c, n_qtiles, T, n_ctas) <= u_lo < span_begin(c + 1, n_qtiles, T, n_ctas)
     found = []
     while c < n_ctas:
         s0, s1 = span_begin(c, n_qtiles, T, n_ctas), span_begin(c + 1, n_qtiles, T, n_ctas)
