@@ -152,7 +152,10 @@ def test_full_size_properties_1m_rows():
     np.testing.assert_array_equal(dot[:48].cpu().numpy(), odot)
 
 
-@pytest.mark.parametrize("n,q", [(420_000, 2500), (301_000, 2100)])
+# the three seeding paths of the screen (csrc/topk.cu run_screen / screen_stages): 420 000 and 301 000 rows seed with the
+# tiled exact kernel (832 / 608 rows), 1 200 000 rows with the 16-rows-per-lane selection kernel (320 rows), 600 000 with
+# the 8-rows-per-lane one (256 rows)
+@pytest.mark.parametrize("n,q", [(420_000, 2500), (301_000, 2100), (1_200_000, 2100), (600_000, 2300)])
 def test_tensor_core_screen_equals_exact_kernel_incl_overflow_fallback(n, q):
     """for batched searches (N >= 65 536, Q >= 2048) ebsd_topk screens with tensor cores and re-ranks the survivors with the
     canonical arithmetic.  Its lists must equal the CUDA-core kernel's bit for bit -- also for queries whose k-th best
