@@ -118,4 +118,13 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// Programmatic dependent launch (the encoder chain: a kernel launched with the programmatic-stream-serialization
+// attribute may become resident while its predecessor still runs).  griddep_launch_dependents: this CTA no longer
+// objects to the NEXT kernel's CTAs being scheduled (they take SMs as this grid's CTAs exit and run their prologue:
+// barrier init, TMEM allocation, weight loads).  griddep_wait: blocks until the PREVIOUS grid has completed and its
+// memory is visible -- every thread executes it before touching anything an earlier kernel of the chain wrote or
+// still reads.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace ebsd

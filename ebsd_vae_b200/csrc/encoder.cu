@@ -163,6 +163,39 @@ int make_src_map(CUtensorMap *map, const float *base, int cin, int w, int nimg, 
     return EBSD_OK;
 }
 
+// Programmatic dependent launch for the kernels of the chain (common.cuh: griddep_wait / griddep_launch_dependents).
+// EBSD_ENCODER_PDL=0 launches them fully serialised (A/B timing only; the results are identical).
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("EBSD_ENCODER_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+void add_pdl_attr(cudaLaunchAttribute *attr, unsigned &n) {
+    if (!pdl_enabled()) return;
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+}
+
+// <<<grid, block, 0, st>>> with the programmatic-serialization attribute
+template <class... KArgs, class... Args>
+cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    unsigned n = 0;
+    add_pdl_attr(attr, n);
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <int CIN, int COUT, int W, int SRC, bool POOL>
 int launch_fused(const ebsd_encoder *enc, int layer, const void *src, const double *src_sums, int src_plane,
                  float *raw, double *sums, int nimg, cudaStream_t st) {
@@ -205,7 +238,7 @@ int launch_fused(const ebsd_encoder *enc, int layer, const void *src, const doub
     cfg.blockDim = dim3(C::THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = C::CL;
     attr[0].val.clusterDim.y = 1;
@@ -231,6 +264,7 @@ int launch_fused(const ebsd_encoder *enc, int layer, const void *src, const doub
     int grid = (p.nitems + per - 1) / per;
     grid = (grid + C::CL - 1) / C::CL * C::CL;
     cfg.gridDim = dim3(grid);
+    add_pdl_attr(attr, cfg.numAttrs);   // after the occupancy query above, which does not take it
     EBSD_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_fused_kernel<CIN, COUT, W, SRC, POOL>, enc->w_map[layer], map_out, map_src, p));
     EBSD_LAUNCH_CHECK();
     return EBSD_OK;
@@ -285,7 +319,7 @@ int launch_front(const ebsd_encoder *enc, const void *pats, const double *sums0,
     const int sms = sm_count();
     const int per = (p.nitems + sms - 1) / sms;
     const int grid = (p.nitems + per - 1) / per;
-    front_u8_kernel<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map_pat, map_out, p);
+    EBSD_CUDA_TRY(launch_chain(front_u8_kernel, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, map_pat, map_out, p));
     EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }
@@ -316,9 +350,12 @@ int fused_dispatch(const ebsd_encoder *enc, int layer, int dtype, const void *sr
 int conv0_stats(const ebsd_encoder *enc, const void *pats, int dtype, int nimg, double *sums0, cudaStream_t st) {
     // uint8: exact integer autocorrelation (patterns must be 4-byte aligned); float32: conv0 recomputed on CUDA cores
     if (dtype == EBSD_PATTERN_U8 && ((uintptr_t)pats & 3) == 0)
-        conv0_stats_u8_kernel<<<nimg, 256, 0, st>>>((const uint8_t *)pats, enc->w0, sums0);
-    else if (dtype == EBSD_PATTERN_U8) conv0_stats_kernel<true><<<dim3(16, nimg), 256, 0, st>>>(pats, enc->w0, sums0);
-    else conv0_stats_kernel<false><<<dim3(16, nimg), 256, 0, st>>>(pats, enc->w0, sums0);
+        EBSD_CUDA_TRY(launch_chain(conv0_stats_u8_kernel, dim3(nimg), dim3(256), 0, st, (const uint8_t *)pats,
+                                   (const float *)enc->w0, sums0));
+    else if (dtype == EBSD_PATTERN_U8)
+        EBSD_CUDA_TRY(launch_chain(conv0_stats_kernel<true>, dim3(16, nimg), dim3(256), 0, st, pats, (const float *)enc->w0, sums0));
+    else
+        EBSD_CUDA_TRY(launch_chain(conv0_stats_kernel<false>, dim3(16, nimg), dim3(256), 0, st, pats, (const float *)enc->w0, sums0));
     EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }
@@ -351,7 +388,8 @@ int forward_chunk_fused(const ebsd_encoder *enc, const void *pin, int dtype, int
             return rc;
         src = dst;
     }
-    heads_norm_kernel<<<nimg, 256, 0, st>>>(src, layer_sums(EBSD_N_CONV - 1, 0), enc->wh, enc->bh, mu, logvar);
+    EBSD_CUDA_TRY(launch_chain(heads_norm_kernel, dim3(nimg), dim3(256), 0, st, src, (const double *)layer_sums(EBSD_N_CONV - 1, 0),
+                               (const float *)enc->wh, (const float *)enc->bh, mu, logvar));
     EBSD_LAUNCH_CHECK();
     return EBSD_OK;
 }

@@ -159,8 +159,10 @@ __global__ void __launch_bounds__(256) conv0_stats_kernel(const void *__restrict
                                                           const float *__restrict__ w0, double *__restrict__ sums) {
     __shared__ float ws[9 * 32];
     __shared__ float red[8][32][2];
+    griddep_launch_dependents();
     for (int i = threadIdx.x; i < 9 * 32; i += 256) ws[i] = w0[i];
     __syncthreads();
+    griddep_wait();   // sums is accumulated atomically and was zeroed by earlier work of the stream
     const long long n = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y = blockIdx.x * 8 + warp, x0 = lane * 4;

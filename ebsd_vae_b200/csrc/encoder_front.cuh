@@ -155,6 +155,7 @@ front_u8_kernel(const __grid_constant__ CUtensorMap map_pat, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    griddep_launch_dependents();   // the next block's CTAs may take SMs as soon as this grid's CTAs leave them
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::A_STAGES; ++s) {
@@ -205,6 +206,21 @@ front_u8_kernel(const __grid_constant__ CUtensorMap map_pat, const __grid_consta
         y0 = yb * 16;
         x0 = (r - yb * C::ITEMS_X) * 8 * C::NT;
     };
+
+    // Programmatic dependent launch: the prologue above and the weight image (written once at create time) overlap the
+    // tail of the kernel in front (the conv0 statistics); nothing below the wait runs before that kernel has completed.
+    if (warp == 18) {
+        if (elect_one_sync() && n_items > 0) {
+            if (FRONT_DBG(p, 8)) {
+                mbar_arrive(w_full);
+            } else {
+                mbar_expect_tx(w_full, C::W_BYTES);
+                bulk_load_1d(smem_u + C::OFF_W, p.weights, C::W_BYTES, w_full);
+            }
+        }
+        __syncwarp();
+    }
+    griddep_wait();
 
     if (warp == 19) {
         // ===================== MMA issuer
@@ -307,14 +323,8 @@ front_u8_kernel(const __grid_constant__ CUtensorMap map_pat, const __grid_consta
             }
         }
     } else if (warp == 18) {
-        // ===================== TMA: the weight image once, then one uint8 patch per item, NPATCH items ahead
+        // ===================== TMA: one uint8 patch per item, NPATCH items ahead (the weight image was requested above)
         if (elect_one_sync() && n_items > 0) {
-            if (FRONT_DBG(p, 8)) {
-                mbar_arrive(w_full);
-            } else {
-                mbar_expect_tx(w_full, C::W_BYTES);
-                bulk_load_1d(smem_u + C::OFF_W, p.weights, C::W_BYTES, w_full);
-            }
             for (int j = 0; j < n_items; ++j) {
                 const int pb = j % C::NPATCH;
                 mbar_wait_bounded(&patch_empty[pb], ((unsigned)(j / C::NPATCH) & 1u) ^ 1u);

@@ -378,6 +378,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    griddep_launch_dependents();   // the next block's CTAs may take SMs as soon as this grid's CTAs leave them
 
     // PAIR: signals towards the leader's MMA issuer are collected LOCALLY in each CTA (one CTA-scope arrival per producer
     // / epilogue warp) and the follower forwards each completed phase with ONE cluster-scope arrival from its otherwise
@@ -428,6 +429,30 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     const int item_end = C::CL > 1 ? item_begin + per_cta
                                    : (item_begin + per_cta < p.nitems ? item_begin + per_cta : p.nitems);
 
+    // one weight tile: a whole [w_fp16; w_fp8] box, or (PAIR) this CTA's halves of the two as boxes of COUT/2
+    // rows, with the bytes of both CTAs credited to the leader's barrier
+    auto load_weights = [&](uint8_t *dst_ptr, int kb, uint64_t *bar) {
+        if (!C::PAIR) {
+            mbar_expect_tx(bar, C::B_TILE);
+            tma_load_2d(dst_ptr, &map_w, 0, kb * 2 * COUT, bar);
+        } else {
+            if (cta_rank == 0) mbar_expect_tx(bar, 2 * C::B_CTA);
+            const int row0 = kb * 2 * COUT;
+            const uint32_t dst = smem_u32(dst_ptr);
+            const uint32_t lbar = map_to_cta(smem_u32(bar), 0);
+            tma_load_2d_pair(dst, &map_w, 0, row0 + (int)cta_rank * (COUT / 2), lbar);
+            tma_load_2d_pair(dst + C::B_X, &map_w, 0, row0 + COUT + (int)cta_rank * (COUT / 2), lbar);
+        }
+    };
+    // Programmatic dependent launch: everything above (and the resident weights, which no kernel of the chain writes)
+    // overlaps the tail of the previous block's kernel; nothing below the wait runs before that kernel has completed.
+    if (C::RESIDENT_B && warp == 0) {
+        if (elect_one_sync())
+            for (int kb = 0; kb < 9 * C::NCHUNK; ++kb) load_weights(smem_b + kb * C::B_CTA, kb, &b_full[kb]);
+        __syncwarp();
+    }
+    griddep_wait();
+
     if (warp == 0) {
         // ===================== weight loads (TMA) + L2 prefetch of the windows the producers will read
         if (elect_one_sync()) {
@@ -457,23 +482,7 @@ conv3x3_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
                 tma_prefetch_l2_4d(&map_src, 0, x0, y0, n);
             };
             for (int j = 0; j < PF + (C::RESIDENT_B ? C::A_STAGES : 0); ++j) prefetch_item(item_begin + j);
-            // one weight tile: a whole [w_fp16; w_fp8] box, or (PAIR) this CTA's halves of the two as boxes of COUT/2
-            // rows, with the bytes of both CTAs credited to the leader's barrier
-            auto load_weights = [&](uint8_t *dst_ptr, int kb, uint64_t *bar) {
-                if (!C::PAIR) {
-                    mbar_expect_tx(bar, C::B_TILE);
-                    tma_load_2d(dst_ptr, &map_w, 0, kb * 2 * COUT, bar);
-                } else {
-                    if (cta_rank == 0) mbar_expect_tx(bar, 2 * C::B_CTA);
-                    const int row0 = kb * 2 * COUT;
-                    const uint32_t dst = smem_u32(dst_ptr);
-                    const uint32_t lbar = map_to_cta(smem_u32(bar), 0);
-                    tma_load_2d_pair(dst, &map_w, 0, row0 + (int)cta_rank * (COUT / 2), lbar);
-                    tma_load_2d_pair(dst + C::B_X, &map_w, 0, row0 + COUT + (int)cta_rank * (COUT / 2), lbar);
-                }
-            };
             if (C::RESIDENT_B) {
-                for (int kb = 0; kb < 9 * C::NCHUNK; ++kb) load_weights(smem_b + kb * C::B_CTA, kb, &b_full[kb]);
                 if (!C::FIRST) {
                     // pace the prefetches with the windows being consumed (a_empty arrives in both CTAs of a pair)
                     unsigned ait = 0;
@@ -1255,6 +1264,8 @@ __global__ void __launch_bounds__(256) conv0_stats_u8_kernel(const uint8_t *__re
                                                              double *__restrict__ sums0) {
     __shared__ unsigned red[8][54];
     __shared__ unsigned tot[54];
+    griddep_launch_dependents();
+    griddep_wait();   // sums0 was zeroed / read by earlier work of the stream
     const long long n = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned *img = (const unsigned *)(pats + n * 16384);
@@ -1328,6 +1339,8 @@ __global__ void __launch_bounds__(256) heads_norm_kernel(const float *__restrict
                                                          float *__restrict__ mu, float *__restrict__ logvar) {
     __shared__ float feat[2048];
     __shared__ float2 tb[128];
+    griddep_launch_dependents();
+    griddep_wait();   // raw9 / sums9 come from the last block's kernel
     const long long n = blockIdx.x;
     if (threadIdx.x < 128) {
         const double *q = sums9 + (n * 128 + threadIdx.x) * 2;
