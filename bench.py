@@ -326,6 +326,47 @@ def cpu_baseline_sample():
     }
 
 
+def chroma_hnsw_recall(dict_hat, queries_hat, exact_idx):
+    """Recall@k of the reference's approximate search (Chroma = hnswlib, cosine space, chromadb 0.6.3 defaults M = 16,
+    construction_ef = 100, search_ef = 10) against this repository's exact lists, on the bench's own dictionary and the
+    first queries of the step.  chromadb / chroma-hnswlib are not installable here, so the index is oracle/hnsw_ref.c,
+    a restatement of hnswlib's published algorithm (parity unpinned, see its header)."""
+    import time
+
+    import numpy as np
+
+    from oracle import hnsw_ref
+
+    t0 = time.perf_counter()
+    index = hnsw_ref.HnswIndex(dict_hat)
+    t_build = time.perf_counter() - t0
+    out = {"kind": "port (oracle/hnsw_ref.c restates hnswlib 0.7.6 HierarchicalNSW; chromadb itself is unavailable; "
+                   "parity unpinned)",
+           "dictionary_rows": int(dict_hat.shape[0]), "queries": int(queries_hat.shape[0]), "k": int(exact_idx.shape[1]),
+           "M": hnsw_ref.CHROMA_M, "construction_ef": hnsw_ref.CHROMA_EF_CONSTRUCTION,
+           "build_rows_per_s_one_thread": dict_hat.shape[0] / t_build}
+    k = exact_idx.shape[1]
+    for ef in (hnsw_ref.CHROMA_EF_SEARCH, 100):
+        t0 = time.perf_counter()
+        _, idx = index.search(queries_hat, k, ef=ef, nthreads=1)
+        dt = time.perf_counter() - t0
+        out["recall_at_%d_search_ef_%d" % (k, ef)] = hnsw_ref.recall_at_k(idx, exact_idx)
+        out["queries_per_s_one_thread_search_ef_%d" % ef] = queries_hat.shape[0] / dt
+    # queries close to a dictionary row (a measured pattern of an orientation the dictionary holds)
+    rng = np.random.default_rng(99)
+    near = dict_hat[rng.integers(0, dict_hat.shape[0], 1024)] + 0.05 * rng.normal(size=(1024, dict_hat.shape[1])).astype(np.float32)
+    near /= np.linalg.norm(near, axis=1, keepdims=True)
+    from oracle import topk_ref
+
+    _, ex_near = topk_ref.topk(dict_hat, near.astype(np.float32), k, nthreads=0)
+    _, idx = index.search(near.astype(np.float32), k, ef=hnsw_ref.CHROMA_EF_SEARCH)
+    out["recall_at_%d_search_ef_%d_near_duplicate_queries" % (k, hnsw_ref.CHROMA_EF_SEARCH)] = hnsw_ref.recall_at_k(idx, ex_near)
+    out["note"] = ("search_ef = %d is chromadb 0.6.3's default (hnswlib uses max(ef, k)); this repository's search is "
+                   "exact (recall 1.0 by construction, checked against float64 above)" % hnsw_ref.CHROMA_EF_SEARCH)
+    index.close()
+    return out
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_gpu(args, rank: int, local_rank: int, world: int):
     import numpy as np
@@ -535,6 +576,12 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
     search_quality = {"exact_fp32_vs_float64_recall_at_%d" % TOP_N: hit, "sample_queries": n_s,
                       "reference_chroma_hnsw_recall": chroma_note}
     del d64, ref64
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not CUSTOM_WORKLOAD:
+        # the reference's DEFAULT dictionary is Chroma's approximate HNSW index: its recall against the exact lists,
+        # from the CPU restatement of hnswlib (oracle/hnsw_ref.c; checker code, runs on the host cores)
+        search_quality["reference_chroma_hnsw_recall_port"] = chroma_hnsw_recall(
+            db._latents[: db.get_count()].cpu().numpy(), qh[:1024].cpu().numpy(),
+            db.search_device(qh[:1024].contiguous(), TOP_N)[1].cpu().numpy() - db.index_base)
 
     # ------------------------------------------------------------------ N > 1: the NCCL path against one rank's search
     def sharded_parity(the_db, qh_local, n_sample=256):
