@@ -607,6 +607,31 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
 
     nccl_parity = sharded_parity(db, qh) if world > 1 else None
 
+    def replicated_record(the_db, idx_sharded, qh_local, steps):
+        """The same step with the normalised rows replicated on every GPU (ShardedLatentVectorDatabase.replicate_rows:
+        64 B per row fetched once): a rank searches only its own queries against ALL rows and no collective is left in
+        the step.  Extra evidence, not the headline -- the headline keeps SURVEY 8e's row-sharded exchange."""
+        t0 = time.perf_counter()
+        the_db.replicate_rows()
+        torch.cuda.synchronize()
+        t_rep = time.perf_counter() - t0
+        _, idx_r, _ = the_db.search_global(qh_local, TOP_N)
+        same = torch.tensor([0 if torch.equal(idx_r, idx_sharded) else 1], device=device)
+        dist.all_reduce(same)
+        if int(same.item()):
+            raise AssertionError(f"rank {rank}: replicated-row search differs from the row-sharded search")
+        for _ in range(2):
+            device_step(the_db)
+        ms = timed(lambda: device_step(the_db), steps) / steps
+        rec = {"rows_per_gpu": int(the_db._replica.shape[0]), "replicate_seconds_once": max_over_ranks(t_rep),
+               "value": q_global / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+               "search_ms": stage_ms(lambda: the_db.search_global(qh_local, TOP_N), reps=5),
+               "identical_to_row_sharded": True, "collectives_per_step": 0}
+        the_db._replica, the_db.replicate = None, False
+        return rec
+
+    replicated = replicated_record(db, idx_own, qh, max(3, min(args.steps, 5))) if world > 1 else None
+
     # ------------------------------------------------------------------ north star: 10 M-row dictionary over N GPUs
     north = None
     if not CUSTOM_WORKLOAD:
@@ -664,6 +689,8 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
         }
         if nccl_parity is not None:
             line["nccl_parity"] = nccl_parity
+        if replicated is not None:
+            line["replicated_dictionary"] = replicated
         if north is not None:
             line["north_star_c4"] = north
         if sweeps is not None:

@@ -12,6 +12,12 @@ bit for bit (asserted on hardware by bench.py at N > 1 and tests/test_gpu_sharde
 plain NCCL calls issued on the compute stream, without host synchronisation when the caller passes the per-rank query
 counts; the exchanged volume (Q*k*8 B per rank) is tiny next to the search itself.
 
+``replicate=True`` (or ``replicate_rows()``) trades memory for the exchange: every rank fetches ALL normalised rows
+once at build time (64 B per row; 10 M rows = 640 MB of a 180 GB GPU) and a query batch then needs no collective at
+all -- each rank searches only its own queries against the full dictionary.  The pair count per rank is the same
+(Q/G x N instead of Q x N/G) but the search runs in its better shape (long dictionary, fewer queries) and the global
+row numbers, hence the results, are the same bit for bit.  The default stays row-sharded.
+
 The plumbing below is backend-agnostic (NCCL on GPUs, gloo in the CPU tests); the search / merge / consensus
 calls are the native kernels and need a GPU.
 """
@@ -86,10 +92,12 @@ class ShardedLatentVectorDatabase(LatentVectorDatabase):
     results; they are collective calls (every rank must make them, possibly with zero queries).
     """
 
-    def __init__(self, config: LatentVectorDatabaseConfig | None = None, group=None) -> None:
+    def __init__(self, config: LatentVectorDatabaseConfig | None = None, group=None, replicate: bool = False) -> None:
         if not dist.is_initialized():
             raise RuntimeError("ShardedLatentVectorDatabase needs torch.distributed to be initialised")
         self.group = group
+        self.replicate = bool(replicate)
+        self._replica: torch.Tensor | None = None   # [N_global,16] normalised rows of every shard, in global row order
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self._global_eulers: torch.Tensor | None = None
@@ -120,6 +128,18 @@ class ShardedLatentVectorDatabase(LatentVectorDatabase):
             qua = torch.zeros((0, 4), dtype=torch.float64, device=dev)
         self._global_eulers = all_gather_rows(eul, self._shard_counts, self.group)
         self._global_quats = all_gather_rows(qua, self._shard_counts, self.group)
+        self._replica = None
+        if self.replicate:
+            self.replicate_rows()
+
+    def replicate_rows(self) -> None:
+        """Collective: fetch the normalised rows of every shard (one all-gather of 64 B per row).  Afterwards a query
+        batch is searched against the full dictionary on the rank that owns it, with no per-batch collective."""
+        dev = self._dev()
+        mine = (self._latents[: self._count] if self._count
+                else torch.zeros((0, self.dimension), dtype=torch.float32, device=dev))
+        self._replica = all_gather_rows(mine, self._shard_counts, self.group).contiguous()
+        self.replicate = True
 
     def add_vectors(self, latent_vectors, orientations, batch_size: int = 1000) -> None:
         if self._count:
@@ -136,6 +156,7 @@ class ShardedLatentVectorDatabase(LatentVectorDatabase):
         self._shard_counts = [0] * self.world
         self.index_base = 0
         self._global_eulers = self._global_quats = None
+        self._replica = None
 
     def _global_count(self) -> int:
         return sum(self._shard_counts)
@@ -160,6 +181,8 @@ class ShardedLatentVectorDatabase(LatentVectorDatabase):
         dev = self._dev()
         lib = _native.load()
         nq = q_hat_local.shape[0]
+        if self._replica is not None:   # replicated rows: the own queries against every row, no collective
+            return self.search_device(q_hat_local, k, rows=self._replica, index_base=0)
         if q_counts is None:
             q_counts = all_gather_counts(nq, self.group, dev)
         elif len(q_counts) != self.world or q_counts[self.rank] != nq:

@@ -325,26 +325,31 @@ class LatentVectorDatabase:
                                                                  self._stream(dev)), "ebsd_normalize_rows")
         return q
 
-    def search_device(self, q_hat: torch.Tensor, k: int):
-        """Exact top-k of normalised queries [Q,16] (CUDA) against the local rows.
+    def search_device(self, q_hat: torch.Tensor, k: int, rows: torch.Tensor | None = None, index_base: int | None = None):
+        """Exact top-k of normalised queries [Q,16] (CUDA) against the local rows (or against ``rows``, normalised
+        [N,16] on the same device, whose row 0 is global row ``index_base``).
 
         Returns (dot [Q,k] f32, idx [Q,k] i64 global rows or -1, dist [Q,k] f32 = 1 - dot), all on the device.
         """
         dev = self._dev()
         lib = _native.load()
         nq = q_hat.shape[0]
+        if rows is None:
+            rows, count, base = self._latents, self._count, self.index_base
+        else:
+            count, base = int(rows.shape[0]), int(index_base or 0)
         dot = torch.empty((nq, k), dtype=torch.float32, device=dev)
         idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
         dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
         if nq == 0:
             return dot, idx, dist
         with torch.cuda.device(dev):   # the plan behind the workspace size depends on the CURRENT device's SM count
-            need = int(lib.ebsd_topk_workspace_bytes(self._count, nq, k))
+            need = int(lib.ebsd_topk_workspace_bytes(count, nq, k))
             if need and (self._topk_ws is None or self._topk_ws.numel() < need):
                 self._topk_ws = torch.empty(need, dtype=torch.uint8, device=dev)
             _native.check(
                 lib.ebsd_topk(
-                    self._latents.data_ptr() if self._count else None, self._count, self.index_base,
+                    rows.data_ptr() if count else None, count, base,
                     q_hat.data_ptr(), nq, k, dot.data_ptr(), idx.data_ptr(), dist.data_ptr(),
                     self._topk_ws.data_ptr() if need else None, need, self._stream(dev)),
                 "ebsd_topk",

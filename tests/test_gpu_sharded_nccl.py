@@ -72,6 +72,23 @@ def _worker(rank, world, port, out_dir):
             np.testing.assert_array_equal(res_g.mean_orientations, res_1.mean_orientations)
             np.testing.assert_array_equal(res_g.similar_masks, res_1.similar_masks)
 
+        # replicated rows: every rank holds all normalised rows and searches only its own queries, without any
+        # per-batch collective -- same global rows, same lists, bit for bit
+        db.replicate_rows()
+        assert tuple(db._replica.shape) == (n_all, 16) and torch.equal(db._replica, single._latents[:n_all])
+        for q_counts in ([3000, 2100], [2500, 0], [1, 1]):
+            nq, a = q_counts[rank], sum(q_counts[:rank])
+            qs = (lat[rng.integers(0, n_all, size=sum(q_counts))] + 0.05 * rng.normal(size=(sum(q_counts), 16)).astype(np.float32))[a : a + nq]
+            qh = db._prepare_queries(torch.from_numpy(qs.reshape(-1, 16)))
+            dot_g, idx_g, dist_g = db.search_global(qh, k)      # no counts needed: nothing is exchanged
+            dot_1, idx_1, dist_1 = single.search_device(single._prepare_queries(torch.from_numpy(qs.reshape(-1, 16))), k)
+            assert torch.equal(idx_g, idx_1) and torch.equal(dot_g, dot_1) and torch.equal(dist_g, dist_1)
+            res_g = db.find_best_orientations_batch(qs.reshape(-1, 16), top_n=k, orientation_threshold=3.0, min_required_matches=3)
+            res_1 = single.find_best_orientations_batch(qs.reshape(-1, 16), top_n=k, orientation_threshold=3.0, min_required_matches=3)
+            np.testing.assert_array_equal(res_g.indices, res_1.indices)
+            np.testing.assert_array_equal(res_g.mean_orientations, res_1.mean_orientations)
+        db._replica, db.replicate = None, False             # back to the row-sharded search for the rest of the test
+
         # query_similar is global too (collective)
         got = db.query_similar(lat[7], n_results=5)
         want = single.query_similar(lat[7], n_results=5)
