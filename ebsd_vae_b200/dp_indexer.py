@@ -300,7 +300,10 @@ class DiffractionPatternIndexer:
         """Index a diffraction pattern and return the best orientation (dp_indexer.py:188-214)."""
         top_n = top_n or self.config.top_n
         orientation_threshold = orientation_threshold or self.config.orientation_threshold
-        latent_vector = self.encode_pattern(pattern)
+        if isinstance(self.db, LatentVectorDatabase):
+            latent_vector = self._encode_any(pattern)[0]   # stays on the device: one synchronisation per pattern, not two
+        else:                                              # a duck-typed dictionary (e.g. the reference's own classes)
+            latent_vector = self.encode_pattern(pattern)
         return self.db.find_best_orientation(
             latent_vector, top_n=top_n, orientation_threshold=orientation_threshold
         )

@@ -480,8 +480,12 @@ class LatentVectorDatabase:
 
     def find_best_orientation(self, query_vector, top_n: int = 20, orientation_threshold: float = 1.0,
                               min_required_matches: int = 18, max_iterations: int = 3) -> OrientationResult:
-        """Find the best matching orientation for one query vector (chroma_db.py:261-342)."""
-        qv = np.asarray(query_vector)
+        """Find the best matching orientation for one query vector (chroma_db.py:261-342).
+
+        A CUDA tensor is taken as it is (``index_pattern`` hands over the encoder's output without a round trip through
+        the host); the result then carries its host copy as ``query_vector``."""
+        on_device = isinstance(query_vector, torch.Tensor) and query_vector.is_cuda
+        qv = query_vector.detach().reshape(-1) if on_device else np.asarray(query_vector)
         if qv.ndim > 1:
             qv = qv.squeeze()
         if qv.shape[0] != self.dimension:
@@ -490,7 +494,8 @@ class LatentVectorDatabase:
                                                   min_required_matches=min_required_matches,
                                                   max_iterations=max_iterations)
         res = batch[0]
-        res.query_vector = query_vector
+        if not on_device:
+            res.query_vector = query_vector
         if not res.success:
             logger.warning("Failed to find best orientation after %d iterations", max_iterations)
         return res

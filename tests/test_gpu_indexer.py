@@ -80,6 +80,14 @@ def test_index_pattern_reference_defaults(setup):
     assert len(set(map(tuple, res.candidate_orientations)) & set(map(tuple, angles[oidx[0]]))) >= 9
     np.testing.assert_allclose(res.distances, 1.0 - odot[0], atol=2e-3)
     assert list(res.similar_indices) == list(range(10))  # radian threshold 3.0 lets every candidate through
+    # the latent stays on the device inside index_pattern; the result still carries the host vector the reference
+    # passes along (dp_indexer.py:210-214), and the two-call form gives the same answer
+    lat = indexer.encode_pattern(patterns[5])
+    assert isinstance(res.query_vector, np.ndarray) and res.query_vector.shape == (16,)
+    np.testing.assert_array_equal(res.query_vector, lat)
+    two = indexer.db.find_best_orientation(lat, top_n=10, orientation_threshold=indexer.config.orientation_threshold)
+    np.testing.assert_array_equal(two.candidate_orientations, res.candidate_orientations)
+    np.testing.assert_array_equal(two.distances, res.distances)
 
 
 def test_search_on_reference_latents_is_bit_exact(setup):
