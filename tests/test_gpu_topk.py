@@ -231,3 +231,32 @@ def test_screen_workspace_covers_every_query_chunk():
     tail = qh[131_072:131_072 + 1500].contiguous()                     # Q < 2048 -> CUDA-core kernel
     dot_e, idx_e, _ = db.search_device(tail, k)
     assert torch.equal(idx[131_072:131_072 + 1500], idx_e) and torch.equal(dot[131_072:131_072 + 1500], dot_e)
+
+
+def test_search_equals_the_reference_faiss_call_path(golden_dir):
+    """tests/golden/faiss_query.npz = the unmodified FaissLatentVectorDatabase.add_vectors / query_similar
+    (latice/index/faiss_db.py:161-193, 216-256) over an exact float32 inner-product stand-in for the faiss wheel:
+    the GPU dictionary returns the same rows in the same order (duplicates: lower id first), inner products within
+    2e-6, for un-normalised rows, a zero row, a zero query, and fewer rows than n_results."""
+    import os
+
+    import ebsd_vae_b200 as E
+
+    g = np.load(os.path.join(golden_dir, "faiss_query.npz"))
+    db = E.LatentVectorDatabase(E.LatentVectorDatabaseConfig(persist_directory=None, mode="faiss"))
+    db.add_vectors(g["latents"], g["orientations"])
+    _, dot, idx, dist = _search(db, g["queries"].astype(np.float32), 10)
+    np.testing.assert_array_equal(idx, g["idx"])
+    np.testing.assert_allclose(dot, g["sims"], rtol=0, atol=2e-6)
+    # the batch surface in FAISS semantics carries the inner products as `distances` (faiss_db.py:241-256, 281-300)
+    res = db.find_best_orientations_batch(g["queries"], top_n=10, orientation_threshold=3.0, min_required_matches=3)
+    np.testing.assert_array_equal(res.indices, g["idx"])
+    np.testing.assert_allclose(res.distances, g["sims"], rtol=0, atol=2e-6)
+    np.testing.assert_array_equal(res.candidate_orientations[5], g["orientations"][g["idx"][5]])
+    # single-query call, Chroma-shaped: ids name the same rows
+    one = db.query_similar(g["queries"][3], n_results=10)
+    assert one["ids"][0] == [f"vec_{i}" for i in g["idx"][3]]
+    small = E.LatentVectorDatabase(E.LatentVectorDatabaseConfig(persist_directory=None, mode="faiss"))
+    small.add_vectors(g["latents"][:4], g["orientations"][:4])
+    got = small.query_similar(g["queries"][0], n_results=10)       # fewer rows than n_results: all of them
+    assert got["ids"][0] == [f"vec_{i}" for i in g["small_idx"]]

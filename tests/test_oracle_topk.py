@@ -107,3 +107,40 @@ def test_threads_do_not_change_results():
     b = T.topk(dn, qn, 10, nthreads=4)
     np.testing.assert_array_equal(a[1], b[1])
     np.testing.assert_array_equal(a[0], b[0])
+
+
+def faiss_lists_agree(idx, dots, g_idx, g_sims, rows, queries, tol=2e-6):
+    """Our lists against the golden FAISS-path lists: scores agree within ``tol`` position by position, and a row named
+    by only one of the two lists scores within ``tol`` of the golden k-th (sgemm and the canonical fma chain round the
+    last bits differently, so near-ties may swap).  Returns the number of queries whose row lists differ."""
+    np.testing.assert_allclose(dots, g_sims, rtol=0, atol=tol)
+    differing = 0
+    for q in range(len(idx)):
+        if np.array_equal(idx[q], g_idx[q]):
+            continue
+        differing += 1
+        kth = float(g_sims[q][-1])
+        for row in set(idx[q].tolist()) ^ set(g_idx[q].tolist()):
+            score = float(rows[row].astype(np.float64) @ queries[q].astype(np.float64))
+            assert abs(score - kth) <= tol, (q, row, score, kth)
+    return differing
+
+
+def test_topk_equals_the_reference_faiss_call_path(golden_dir):
+    """tests/golden/faiss_query.npz: the unmodified FaissLatentVectorDatabase.add_vectors / query_similar
+    (latice/index/faiss_db.py:161-193, 216-256) over an exact float32 inner-product stand-in for the faiss wheel
+    (oracle/make_golden_faiss_query.py).  The oracle gives the same rows, scores within 2e-6, incl. the zero row, the
+    zero query, exact duplicates (lower id first) and fewer rows than n_results."""
+    import os
+    g = np.load(os.path.join(golden_dir, "faiss_query.npz"))
+    rows = T.normalize_rows(g["latents"])
+    queries = T.normalize_rows(g["queries"].astype(np.float32))
+    dots, idx = T.topk(rows, queries, 10)
+    swaps = faiss_lists_agree(idx, dots, g["idx"], g["sims"], rows, queries)
+    assert swaps <= 2
+    dup = idx[94]                                     # the query that is 3 x row 17: rows 17, 2000..2003 tie at 1.0
+    assert dup[:5].tolist() == [17, 2000, 2001, 2002, 2003] and g["idx"][94][:5].tolist() == dup[:5].tolist()
+    assert idx[95].tolist() == list(range(10))        # zero query: every score is 0, lowest ids win
+    d4, i4 = T.topk(rows[:4], queries[:1], 4)
+    np.testing.assert_array_equal(i4[0], g["small_idx"])
+    np.testing.assert_allclose(d4[0], g["small_sims"], atol=2e-6)
