@@ -194,3 +194,45 @@ def test_faiss_mode_reports_inner_products_as_distances():
     assert out["chroma"].distances[0] < 1e-3 and (np.diff(out["chroma"].distances) >= 0).all()
     with pytest.raises(ValueError, match="persist_directory is None"):
         db.save()
+
+
+def test_database_reproduces_the_reference_chroma_path_end_to_end(golden_dir):
+    """tests/golden/chroma_path.npz (oracle/make_golden_chroma_path.py): the unmodified ChromaLatentVectorDatabase --
+    two add_vectors calls (id offset), query_similar, find_best_orientation and find_best_orientations_batch with the
+    REAL query feeding the consensus (chroma_db.py:144-410) -- over an exact cosine stand-in for the chromadb
+    collection.  The GPU dictionary gives the same ids, metadata, distances (1 - cos within 3e-7), success flags,
+    similar indices, best and mean orientations."""
+    import os
+
+    import ebsd_vae_b200 as E
+
+    g = np.load(os.path.join(golden_dir, "chroma_path.npz"))
+    thr, mrm, mit = g["params"]
+    db = E.LatentVectorDatabase(E.LatentVectorDatabaseConfig(persist_directory=None))
+    db.add_vectors(g["latents"][:1700], g["orientations"][:1700], batch_size=1000)
+    db.add_vectors(g["latents"][1700:], g["orientations"][1700:], batch_size=512)
+    assert db.get_count() == len(g["latents"])
+    for i in (0, 7, 31):
+        res = db.query_similar(g["queries"][i], n_results=10)
+        assert res["ids"][0] == [f"vec_{j}" for j in g["idx"][i]]
+        np.testing.assert_allclose(res["distances"][0], g["dist"][i], rtol=0, atol=3e-7)
+        assert [m["orientation_str"] for m in res["metadatas"][0]] == list(g["orientation_str"][i])
+        assert [m["phi1"] for m in res["metadatas"][0]] == g["orientations"][g["idx"][i], 0].tolist()
+    batch = db.find_best_orientations_batch(g["queries"], top_n=10, orientation_threshold=float(thr),
+                                            min_required_matches=int(mrm), max_iterations=int(mit))
+    np.testing.assert_array_equal(batch.indices, g["idx"])
+    np.testing.assert_allclose(batch.distances, g["dist"], rtol=0, atol=3e-7)
+    np.testing.assert_array_equal(batch.success, g["success"])
+    np.testing.assert_array_equal(batch.best_orientations, g["best"])
+    ok = g["success"]
+    np.testing.assert_allclose(batch.mean_orientations[ok], g["mean"][ok], atol=1e-6)
+    for i in range(len(batch)):
+        r = batch[i]
+        sim = np.zeros(10, bool)
+        sim[r.similar_indices] = True
+        np.testing.assert_array_equal(sim, g["similar"][i])
+        assert (r.mean_orientation is None) == (not ok[i])
+    one = db.find_best_orientation(g["queries"][2], top_n=10, orientation_threshold=float(thr),
+                                   min_required_matches=int(mrm), max_iterations=int(mit))
+    assert one.success == bool(ok[2])
+    np.testing.assert_array_equal(one.candidate_orientations, g["orientations"][g["idx"][2]])
