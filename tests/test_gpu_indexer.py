@@ -236,3 +236,48 @@ def test_database_reproduces_the_reference_chroma_path_end_to_end(golden_dir):
                                    min_required_matches=int(mrm), max_iterations=int(mit))
     assert one.success == bool(ok[2])
     np.testing.assert_array_equal(one.candidate_orientations, g["orientations"][g["idx"][2]])
+
+
+def test_indexer_reproduces_the_reference_end_to_end(tmp_path, golden_dir):
+    """BASELINE configs[0] through the UNMODIFIED reference (tests/golden/indexer_path.npz, written by
+    oracle/make_golden_indexer_path.py): DiffractionPatternIndexer.build_dictionary from a pattern .npy + angle file
+    (DPDataModule, default transform, latice.model on the CPU), then index_pattern / index_patterns_batch.  The same
+    script against this package gives the same dictionary (latents within 1e-3, angles bit for bit), the same candidate
+    lists, distances within 2e-3, the same success flags and best orientations, mean orientations within 0.1 degree."""
+    import ebsd_vae_b200 as E
+
+    g = np.load(os.path.join(golden_dir, "indexer_path.npz"))
+    thr, mrm, mit = g["params"]
+    np.save(tmp_path / "sample_pattern.npy", (g["k_u8"].astype(np.float64) + 0.5) / 255.0)
+    (tmp_path / "anglefile.txt").write_text(str(g["angle_text"]))
+    model = E.VariationalAutoEncoderRawData()
+    model.load_state_dict(R.make_state_dict(42))
+    cfg = E.IndexerConfig(pattern_path=tmp_path / "sample_pattern.npy", angles_path=tmp_path / "anglefile.txt",
+                          batch_size=16, device="cuda", top_n=10, orientation_threshold=float(thr))
+    indexer = E.DiffractionPatternIndexer(model, db=E.LatentVectorDatabase(E.LatentVectorDatabaseConfig(persist_directory=None)),
+                                          config=cfg)
+    indexer.build_dictionary()
+    n = len(g["k_u8"])
+    assert indexer.db.get_count() == n
+    np.testing.assert_array_equal(indexer.db._eulers[:n].cpu().numpy(), g["dict_angles"])
+    want = g["dict_latents"] / np.linalg.norm(g["dict_latents"], axis=1, keepdims=True)
+    got = indexer.db._latents[:n].cpu().numpy()
+    assert np.linalg.norm(got - want, axis=1).max() < 1e-3
+
+    queries = (g["k_u8"][:12].astype(np.float64) + 0.5) / 255.0
+    lat = indexer.encode_pattern(queries[4])
+    assert np.linalg.norm(lat - g["one_latent"]) / np.linalg.norm(g["one_latent"]) < 1e-3
+    one = indexer.index_pattern(queries[4])                 # the reference's defaults: 18 matches of 10 -> no consensus
+    assert one.success is False and bool(g["one_success"]) is False and one.mean_orientation is None
+    np.testing.assert_array_equal(one.candidate_orientations, g["one_candidates"])
+    np.testing.assert_allclose(one.distances, g["one_distances"], rtol=0, atol=2e-3)
+
+    batch = indexer.index_patterns_batch(queries, top_n=10, orientation_threshold=float(thr),
+                                         min_required_matches=int(mrm), max_iterations=int(mit))
+    assert 0 < g["batch_success"].sum() < len(queries)
+    np.testing.assert_array_equal(batch.success, g["batch_success"])
+    np.testing.assert_array_equal(batch.candidate_orientations, g["batch_candidates"])
+    np.testing.assert_array_equal(batch.best_orientations, g["batch_best"])
+    np.testing.assert_allclose(batch.distances, g["batch_distances"], rtol=0, atol=2e-3)
+    for i in np.flatnonzero(g["batch_success"]):
+        assert _misorientation_deg(batch.mean_orientations[i], g["batch_mean"][i]) < 0.1
