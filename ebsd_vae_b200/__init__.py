@@ -5,6 +5,7 @@ Drop-in names (reference: poyentung/ebsd-vae, package ``latice``):
 * ``DiffractionPatternIndexer``, ``IndexerConfig``           (latice/index/dp_indexer.py)
 * ``LatentVectorDatabase`` (= ``ChromaLatentVectorDatabase``), ``LatentVectorDatabaseConfig``,
   ``OrientationResult``                                      (latice/index/chroma_db.py)
+* ``FaissLatentVectorDatabase``, ``FaissLatentVectorDatabaseConfig``  (latice/index/faiss_db.py)
 * ``VariationalAutoEncoderRawData``                          (latice/model.py)
 * ``get_color_key``                                          (latice/utils/utils.py:206-240, IPF colours)
 
@@ -16,6 +17,8 @@ from .dp_indexer import DiffractionPatternIndexer, IndexerConfig
 from .model import EncoderEngine, VariationalAutoEncoderRawData, load_vae_weights
 from .vector_db import (
     ChromaLatentVectorDatabase,
+    FaissLatentVectorDatabase,
+    FaissLatentVectorDatabaseConfig,
     LatentVectorDatabase,
     LatentVectorDatabaseConfig,
     OrientationResult,
@@ -29,6 +32,8 @@ __all__ = [
     "VariationalAutoEncoderRawData",
     "load_vae_weights",
     "ChromaLatentVectorDatabase",
+    "FaissLatentVectorDatabase",
+    "FaissLatentVectorDatabaseConfig",
     "LatentVectorDatabase",
     "LatentVectorDatabaseConfig",
     "OrientationResult",

@@ -503,3 +503,68 @@ class LatentVectorDatabase:
 
 # Name used by the current reference code (latice/index/chroma_db.py:87); README/notebooks use LatentVectorDatabase.
 ChromaLatentVectorDatabase = LatentVectorDatabase
+
+
+@dataclass
+class FaissLatentVectorDatabaseConfig:
+    """Fields and defaults of latice/index/faiss_db.py:34-46 (plus the CUDA device holding the dictionary)."""
+
+    npz_path: str = "faiss_index.npz"
+    dimension: int = 16
+    device: str = "cuda"
+
+    # what the shared implementation reads from a configuration
+    mode = "faiss"
+
+    @property
+    def collection_name(self) -> str:
+        return Path(self.npz_path).with_suffix("").name
+
+    @property
+    def persist_directory(self) -> str:
+        return str(Path(self.npz_path).parent)
+
+
+class FaissLatentVectorDatabase(LatentVectorDatabase):
+    """Drop-in for the reference's FAISS twin (latice/index/faiss_db.py:92-496): the same exact search and consensus
+    kernels with that class's conventions -- ``query_similar`` returns ``(similarities, indices)`` (inner products,
+    descending) instead of Chroma's dictionary, ``n_results`` is clamped to the row count, an empty index gives empty
+    arrays / a NaN result, thresholds are degrees, ``best_orientation`` is the mean on success, iterations are clamped
+    to the candidates, and the dictionary persists to ONE ``.npz`` (``npz_path``), reopened on construction."""
+
+    def __init__(self, config: FaissLatentVectorDatabaseConfig | None = None) -> None:
+        super().__init__(config if config is not None else FaissLatentVectorDatabaseConfig())
+
+    def query_similar(self, query_vector, n_results: int = 20):
+        """(similarities [k] f32 descending, indices [k] i64) of one query (faiss_db.py:216-256)."""
+        if self.get_count() == 0:
+            logger.warning("Querying an empty index.")
+            return np.array([]), np.array([])
+        if self.get_count() < n_results:
+            logger.warning("Requested %d results, but index only contains %d vectors. Returning all.", n_results,
+                           self.get_count())
+            n_results = self.get_count()
+        query_vector = np.asarray(query_vector)
+        if query_vector.ndim == 1:
+            query_vector = query_vector.reshape(1, -1)
+        if query_vector.shape[1] != self.dimension:
+            raise ValueError(f"Expected query vector of dimension {self.dimension}, got {query_vector.shape[1]}")
+        k = self._clamp_k(n_results)
+        dot, idx, _ = self.search_device(self._prepare_queries(query_vector[:1]), k)
+        dot_h, idx_h = _to_host(dot[0], idx[0])
+        return dot_h.copy(), idx_h.copy()
+
+    def find_best_orientation(self, query_vector, top_n: int = 20, orientation_threshold: float = 1.0,
+                              min_required_matches: int = 18, max_iterations: int = 3) -> OrientationResult:
+        if self.get_count() == 0:   # faiss_db.py:280-291
+            logger.warning("No similar vectors found for query.")
+            return OrientationResult(query_vector=np.asarray(query_vector).squeeze(),
+                                     best_orientation=np.array([np.nan, np.nan, np.nan]),
+                                     candidate_orientations=np.array([]), distances=np.array([]),
+                                     mean_orientation=None, success=False, similar_indices=None)
+        res = super().find_best_orientation(query_vector, top_n=min(top_n, self.get_count()),
+                                            orientation_threshold=orientation_threshold,
+                                            min_required_matches=min_required_matches, max_iterations=max_iterations)
+        if not (isinstance(query_vector, torch.Tensor) and query_vector.is_cuda):
+            res.query_vector = np.asarray(query_vector).squeeze().astype(np.float64)   # faiss_db.py:358-360
+        return res

@@ -260,3 +260,43 @@ def test_search_equals_the_reference_faiss_call_path(golden_dir):
     small.add_vectors(g["latents"][:4], g["orientations"][:4])
     got = small.query_similar(g["queries"][0], n_results=10)       # fewer rows than n_results: all of them
     assert got["ids"][0] == [f"vec_{i}" for i in g["small_idx"]]
+
+
+def test_faiss_twin_class_equals_the_reference_faiss_call_path(golden_dir, tmp_path):
+    """The drop-in FaissLatentVectorDatabase (reference: latice/index/faiss_db.py:92-496) against
+    tests/golden/faiss_query.npz: query_similar returns the reference's (similarities, indices) tuple, clamps n_results
+    to the row count, and the single .npz is reopened by a new object."""
+    import os
+
+    import ebsd_vae_b200 as E
+
+    g = np.load(os.path.join(golden_dir, "faiss_query.npz"))
+    cfg = E.FaissLatentVectorDatabaseConfig(npz_path=str(tmp_path / "faiss_index.npz"))
+    db = E.FaissLatentVectorDatabase(cfg)
+    db.add_vectors(g["latents"], g["orientations"])
+    for i in (0, 50, 94, 95):
+        sims, idx = db.query_similar(g["queries"][i], n_results=10)
+        assert sims.dtype == np.float32 and idx.dtype == np.int64
+        np.testing.assert_array_equal(idx, g["idx"][i])
+        np.testing.assert_allclose(sims, g["sims"][i], rtol=0, atol=2e-6)
+    with pytest.raises(ValueError, match="Expected query vector of dimension 16, got 8"):
+        db.query_similar(np.zeros(8))
+    res = db.find_best_orientation(g["queries"][3], top_n=10, orientation_threshold=30.0, min_required_matches=2)
+    np.testing.assert_array_equal(res.candidate_orientations, g["orientations"][g["idx"][3]])
+    np.testing.assert_allclose(res.distances, g["sims"][3], rtol=0, atol=2e-6)     # FAISS carries inner products
+    assert res.query_vector.dtype == np.float64
+    if res.success:
+        np.testing.assert_array_equal(res.best_orientation, res.mean_orientation)  # faiss_db.py:338-342
+    db.save()
+    again = E.FaissLatentVectorDatabase(cfg)                                       # reopens the file (faiss_db.py:129-130)
+    assert again.get_count() == len(g["latents"])
+    np.testing.assert_array_equal(again.query_similar(g["queries"][7], 10)[1], g["idx"][7])
+    small = E.FaissLatentVectorDatabase(E.FaissLatentVectorDatabaseConfig(npz_path=str(tmp_path / "small.npz")))
+    small.add_vectors(g["latents"][:4], g["orientations"][:4])
+    sims, idx = small.query_similar(g["queries"][0], n_results=10)
+    np.testing.assert_array_equal(idx, g["small_idx"])
+    np.testing.assert_allclose(sims, g["small_sims"], atol=2e-6)
+    r4 = small.find_best_orientation(g["queries"][0], top_n=10)                    # top_n clamps to the 4 rows
+    assert r4.candidate_orientations.shape == (4, 3)
+    again.delete_persistence()
+    assert again.get_count() == 0 and not (tmp_path / "faiss_index.npz").exists()

@@ -176,3 +176,21 @@ def test_copy_slices_cover_the_batch_with_a_short_first_slice():
         assert all(0 < e - a <= D.ENCODE_PASS for a, e in sl)
         if b > D.ENCODE_PASS // 2:
             assert sl[0][1] - sl[0][0] <= (D.ENCODE_PASS + 1) // 2 + 1
+
+
+def test_faiss_twin_names_defaults_and_empty_index(tmp_path):
+    """FaissLatentVectorDatabase / FaissLatentVectorDatabaseConfig keep the reference's names, defaults and its
+    empty-index behaviour (latice/index/faiss_db.py:34-46, 232-234, 280-291) -- no GPU is touched by an empty index."""
+    import ebsd_vae_b200 as E
+
+    cfg = E.FaissLatentVectorDatabaseConfig()
+    assert cfg.npz_path == "faiss_index.npz" and cfg.dimension == 16
+    db = E.FaissLatentVectorDatabase(E.FaissLatentVectorDatabaseConfig(npz_path=str(tmp_path / "store" / "idx.npz")))
+    assert db.get_count() == 0 and db.npz_path == tmp_path / "store" / "idx.npz" and db.config.mode == "faiss"
+    sims, idx = db.query_similar(np.ones(16))
+    assert sims.size == 0 and idx.size == 0
+    res = db.find_best_orientation(np.ones((1, 16)))
+    assert res.success is False and np.isnan(res.best_orientation).all() and res.mean_orientation is None
+    assert res.candidate_orientations.size == 0 and res.similar_indices is None and res.query_vector.shape == (16,)
+    with pytest.raises(FileNotFoundError, match="NPZ file missing."):
+        db.load()
