@@ -273,9 +273,9 @@ def reference_sample(world: int, n_enc: int, n_q: int):
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
-    # >= 3 s of real CPU work per step: 256 patterns through the encoder (~1-2 s on 16-32 threads), 2048 searches and
-    # 2048 consensus calls (~1.5 s of serial numpy)
-    n_enc, n_q = 256, 2048
+    # >= 3 s of real CPU work per step on the GPU box's host (16 threads: 512 patterns through the encoder ~1.9 s,
+    # 4096 searches ~0.2 s, 4096 consensus calls ~1.4 s of serial numpy; the round-2 sample of half that size ran 1.7 s)
+    n_enc, n_q = 512, 4096
     step, cores, n_dict = reference_sample(world, n_enc, n_q)
     for _ in range(min(args.warmup, 1)):
         step()
