@@ -290,15 +290,23 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": len(runs),
         "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3 * N_QUERY_PER_GPU * world, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(world), "dictionary_rows": n_dict, "queries": N_QUERY_PER_GPU * world,
-                   "top_n": TOP_N, "orientation_threshold": THRESHOLD, "min_required_matches": MIN_REQUIRED,
-                   "timing": "ms_per_step is EXTRAPOLATED from a bounded sample (value x queries); the sample itself ran "
-                             f"{wall:.1f} s per step"},
+        "config": bench_config(world),   # the same workload record as the GPU arm's line
+        "timing": "ms_per_step is EXTRAPOLATED from a bounded sample (value x queries); the sample itself ran "
+                  f"{wall:.1f} s per step",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def bench_config(world: int) -> dict:
+    """The workload record both arms print (the reference arm times a bounded sample of exactly this workload)."""
+    return {"workload": workload_name(world), "dictionary_rows": N_DICT_PER_GPU * world,
+            "queries": N_QUERY_PER_GPU * world, "top_n": TOP_N, "orientation_threshold": THRESHOLD,
+            "min_required_matches": MIN_REQUIRED, "weights": "seed-42 random init (vae-best.pt layout)",
+            "l2_policy": "inputs larger than L2 (164 MB of uint8 patterns per step; activations stream)",
+            "parallelism": f"dp{world}+row-sharded dictionary" if world > 1 else "single GPU"}
 
 
 def workload_name(world: int) -> str:
@@ -676,11 +684,7 @@ def run_gpu(args, rank: int, local_rank: int, world: int):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(world), "dictionary_rows": N_DICT_PER_GPU * world,
-                       "queries": q_global, "top_n": TOP_N, "orientation_threshold": THRESHOLD,
-                       "min_required_matches": MIN_REQUIRED, "weights": "seed-42 random init (vae-best.pt layout)",
-                       "l2_policy": "inputs larger than L2 (164 MB of uint8 patterns per step; activations stream)",
-                       "parallelism": f"dp{world}+row-sharded dictionary" if world > 1 else "single GPU"},
+            "config": bench_config(world),
             "e2e": {"value": q_global / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
