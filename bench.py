@@ -7,8 +7,9 @@ A "step" is one pass of the hot path over one batch of synthetic input.  At N = 
 BASELINE.json configs[1]: a 100k-orientation dictionary (16-D latents), 10k query patterns of 128x128, top-10,
 orientation_threshold 3.0.  With N > 1 (torchrun, one rank per GPU) the same per-GPU work is replicated
 (weak scaling): every rank encodes its own 10k patterns, the dictionary is row-sharded (100k rows per rank),
-latents are all-gathered, every rank searches its shard for ALL queries, candidates are all-gathered and
-merged, and each rank runs the consensus for its own queries.
+latents are all-gathered, every rank searches its shard for ALL queries, the packed candidates go through one
+all-to-all and are merged, and each rank runs the consensus for its own queries.  N > 1 lines also carry
+`replicated_dictionary`: the same step with the normalised rows replicated on every GPU (no collective per step).
 
 Every line also carries `north_star_c4` (BASELINE configs[3]: a 10 M-row dictionary row-sharded over the N GPUs, 10k
 patterns per GPU), at N > 1 a hardware parity check of the NCCL-sharded search against a single-rank search of the
@@ -23,6 +24,8 @@ The JSON line carries
   roofline  -- the dominant kernel chain (the encoder convolutions, tensor bound) timed live with CUDA events
   stages    -- per-stage device times and the search kernel's own HBM / FMA figures
   cpu_baseline -- the oracle port timed on this box's host cores on a bounded sample (rank 0, N = 1 only)
+  search_quality -- outside every timed region: the exact lists against a float64 brute force, and the recall@10 of the
+               reference's approximate Chroma/HNSW search from its CPU restatement (oracle/hnsw_ref.c, checker code)
 
 `--impl reference` times the reference's CPU path (restated by oracle/: torch-CPU fp32 encoder, exact cosine
 top-k in C on all host threads, numpy consensus) on bounded samples of the same workload.
